@@ -1,0 +1,201 @@
+/* idiff.h -- C ABI of libidiff_sm100.so: hand-written sm_100a kernels for the InstanceDiff
+ * reverse-SDE hot path (UNet forward + fused Euler-Maruyama update).
+ *
+ * The reference (zyc-123/InstanceDiff) is pure Python/PyTorch and has no FFI of its own; every
+ * entry point below names the reference Python call (file:line) whose device work it replaces.
+ * INTEGRATION.md shows the ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every pointer is a DEVICE
+ * pointer unless the name ends in _host; `stream` is a cudaStream_t passed as void*; calls are
+ * stream-ordered and never synchronise; return 0 on success, a negative idiff_status otherwise
+ * (idiff_last_error() gives the text); nothing throws across the boundary; no CPU fallback.
+ * Activations are channels-last (NHWC) bf16; x / mu / eps / z are fp32 [B,1,H,W].
+ */
+#ifndef IDIFF_H_
+#define IDIFF_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  IDIFF_OK = 0,
+  IDIFF_ERR_ARG = -1,      /* bad shape / null / misaligned pointer */
+  IDIFF_ERR_UNSUPPORTED = -2,
+  IDIFF_ERR_CUDA = -3,     /* a CUDA runtime call failed */
+  IDIFF_ERR_WATCHDOG = -4  /* a device-side pipeline wait timed out (see idiff_watchdog_status) */
+} idiff_status;
+
+int idiff_abi_version(void);
+const char* idiff_last_error(void);
+/* Reads (and optionally clears) the device watchdog word; synchronises the device. 0 = healthy. */
+int idiff_watchdog_status(int clear);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused reverse-SDE Euler-Maruyama update.  Replaces the 12-launch ATen chain of
+ *   IRSDE.score_fn tail / get_score_from_noise   utils/sde_utils.py:187-188,196-199
+ *   IRSDE.sde_reverse_drift                      utils/sde_utils.py:178-179
+ *   IRSDE.dispersion                             utils/sde_utils.py:184-185
+ *   SDE.reverse_sde_step (/_mean)                utils/sde_utils.py:41-46
+ * with one pass that keeps the reference's fp32 operation order (no FMA contraction):
+ *   score = -eps / sigma_bar            (input_is_score != 0: `eps` already holds the score)
+ *   x_out = x - (theta*(mu-x) - sigma^2*score)*dt - sigma*(z*sqrt_dt)
+ * coef points at 5 floats {theta_t, sigma_t, sigma_bar_t, dt, sqrt_dt} in DEVICE memory
+ * (a row of the table written by idiff_sde_pack_table), so one captured CUDA graph can be
+ * replayed for every t.  z == NULL and use_philox == 0 gives the mean-only step (:41-42);
+ * use_philox != 0 draws z in-kernel (Philox4x32-10 + Box-Muller) from (seed, elem_offset + i).
+ * mu may be NULL (the reference's default mu = 0., :152).  x_out may alias x.
+ * ------------------------------------------------------------------------------------------ */
+int idiff_sde_step(float* x_out, const float* x, const float* eps, const float* mu, const float* z,
+                   const float* coef, int input_is_score, int use_philox, uint64_t seed,
+                   uint64_t elem_offset, size_t n, void* stream);
+
+/* Builds the per-t coefficient rows {theta, sigma, sigma_bar, dt, sqrt_dt, 0,0,0} (8 floats per
+ * t, T1 = T+1 rows) from the reference's tables (utils/sde_utils.py:149-152) on the HOST. */
+int idiff_sde_pack_table(const float* theta_host, const float* sigma_host, const float* sigma_bar_host,
+                         int T1, float dt, double sqrt_dt, float* table_out_host);
+
+/* x_T = mu + z * max_sigma            IRSDE.noise_state  utils/sde_utils.py:340-341 */
+int idiff_noise_state(float* x_out, const float* mu, const float* z, float max_sigma, int use_philox,
+                      uint64_t seed, uint64_t elem_offset, size_t n, void* stream);
+
+/* Standard normal draws with the same Philox stream the fused step uses (tests / host parity). */
+int idiff_philox_normal(float* out, uint64_t seed, uint64_t elem_offset, uint32_t step, size_t n, void* stream);
+
+/* Graph-replay support for the loop `for t in reversed(range(1, T+1))` (utils/sde_utils.py:248):
+ * copies table row *t_counter (8 floats) to cur_row, writes the model time t*sample_scale (:198)
+ * to *cur_time and decrements *t_counter -- all on the device, so one captured graph serves all t. */
+int idiff_step_select(const float* table, int* t_counter, float* cur_row, float* cur_time, float sample_scale,
+                      void* stream);
+
+/* Bring-up switches used by tests/test_umma_probe.py only (bit 1: swap LBO/SBO of the MN-major V
+ * descriptor in self-attention; bit 2: swap LBO/SBO of its K-major descriptors). 0 in production. */
+int idiff_set_debug_flags(int flags);
+
+/* ------------------------------------------------------------------------------------------
+ * UNet building blocks (the model callable of IRSDE.score_fn, utils/sde_utils.py:198; network
+ * spec SURVEY.md App. A -- the reference snapshot does not ship models/modules/*).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Implicit-GEMM convolution / linear layer on tcgen05 tensor cores.
+ * out[b,oy,ox,:] = epilogue( sum_{tap,c} W[:,tap,c] * T(src[b, iy, ix, c]) )
+ * One CTA computes a 16x8-pixel x NT-channel tile: the input patch (with halo) is staged once
+ * per 64-channel chunk in shared memory in the UMMA no-swizzle K-major layout and re-used by every
+ * filter tap through shifted matrix descriptors; weights stream in by bulk TMA; fp32
+ * accumulators live in TMEM. */
+typedef struct idiff_gemm_params {
+  /* geometry (OUTPUT grid) */
+  int32_t B, H, W;          /* output pixels */
+  int32_t ksize;            /* 1, 3 (pad 1) or 4 (stride 2, pad 1) */
+  int32_t stride;           /* 1 or 2 (2 only with ksize 4) */
+  int32_t cin0, cin1;       /* channels of the two concatenated sources (multiples of 64; cin1 may be 0) */
+  int32_t up0;              /* 1: BOTH sources are read through nearest x2 upsampling (src at H/2 x W/2) */
+  int32_t N;                /* output channels */
+  int32_t NT;               /* N tile: 64, 128 or 256; N % NT == 0 */
+  int32_t a_silu;           /* apply SiLU after the A affine */
+  int32_t epi;              /* IDIFF_EPI_* */
+  int32_t gn_groups;        /* >0: write GroupNorm partial sums (requires gn_partial) */
+  int32_t out_ld;           /* leading dimension (elements) of out */
+  int32_t dbg_swap_lbo_sbo; /* bring-up switch used by the probe test only */
+  int32_t src0_ld;          /* pixel pitch (elements) of src0 / src1; 0 = cin0 / cin1 */
+  int32_t src1_ld;
+  int32_t reserved0;
+  const void* src0;         /* bf16 NHWC */
+  const void* src1;         /* bf16 NHWC or NULL */
+  const float* a_scale;     /* [B][cin] per-(image,channel) affine applied on load, or NULL */
+  const float* a_shift;
+  const void* w;            /* packed bf16 weights, see instancediff_b200/packing.py */
+  int64_t w_image_stride;   /* elements between per-image weight sets (0 = shared) */
+  const float* bias;        /* [N] or NULL */
+  const float* bias_img;    /* [B][N] or NULL */
+  const float* row_stats;   /* [B*H*W][2] (mean, rstd): acc' = (acc - mean*wsum[n]) * rstd   (LayerNorm fold) */
+  const float* wsum;        /* [N] */
+  const void* res0;         /* bf16 [B*H*W][N] residual or NULL */
+  const void* res1;         /* second residual or NULL */
+  const float* res0_scale;  /* [B][N]: res0 enters as silu(res0*scale+shift) (GroupNorm+SiLU of the block output) */
+  const float* res0_shift;
+  const float* ln_g;        /* IDIFF_EPI_LN_OUT: gain [N] */
+  void* out;                /* bf16 */
+  float* gn_partial;        /* [B][tiles_per_image][gn_groups][2] */
+  float* out_row_stats;     /* [B*H*W][2] LayerNorm stats of the stored row (needs NT == N) */
+  float qscale;             /* IDIFF_EPI_QSOFTMAX: multiplier after the softmax */
+  float ln_eps;
+} idiff_gemm_params;
+
+enum {
+  IDIFF_EPI_PLAIN = 0,
+  IDIFF_EPI_QSOFTMAX = 1,  /* softmax over each 32-column group of columns [0,128), times qscale */
+  IDIFF_EPI_GEGLU = 2,     /* columns interleaved (a,gate): out[j] = a * gelu(gate); out width N/2 */
+  IDIFF_EPI_LN_OUT = 3     /* channel LayerNorm of (acc+bias) * ln_g, then + residuals (needs NT == N) */
+};
+
+int idiff_conv_gemm(const idiff_gemm_params* p, void* stream);
+/* sizeof(idiff_gemm_params) as compiled -- lets a binding verify its struct mirror */
+int idiff_sizeof_gemm_params(void);
+/* shared memory the kernel will request for these params (bytes), or negative status */
+int idiff_conv_gemm_smem_bytes(const idiff_gemm_params* p);
+
+/* Plain CUDA-core convolution over the same params subset (ksize, stride, cin0/cin1, up0, a_*,
+ * bias, PLAIN epilogue, fp32 weights [N][k][k][cin]).  Used for validation of the tensor-core path. */
+int idiff_conv_ref(const idiff_gemm_params* p, const float* w_f32, float* out_f32, void* stream);
+
+/* Stem: cat([x - mu, mu]) -> 7x7 conv (pad 3) -> bf16 NHWC [B,H,W,N].  w: fp32 [N][7][7][2]. */
+int idiff_stem_conv7(const float* x, const float* mu, const float* w, const float* bias, void* out,
+                     int B, int H, int W, int N, void* stream);
+
+/* Head: 3x3 conv C -> 1 channel, fp32 out [B,1,H,W].  w: fp32 [3][3][C]. */
+int idiff_head_conv3(const void* src, const float* w, float bias, float* out, int B, int H, int W, int C,
+                     void* stream);
+
+/* Sinusoidal embedding -> Linear -> GELU -> Linear, then every ResBlock's Linear(SiLU(temb)).
+ * t: [B] fp32 device (t_scalar used when NULL).  w1 [4nf][nf], w2 [4nf][4nf], wss [S][4nf] with
+ * S = sum of 2*cout over all ResBlocks; out_ss [B][S]. */
+int idiff_time_embed(const float* t, float t_scalar, const float* w1, const float* b1, const float* w2,
+                     const float* b2, const float* wss, const float* bss, float* temb_scratch,
+                     float* out_ss, int B, int nf, int S, void* stream);
+
+/* GroupNorm finalize: reduce per-tile partial sums -> per-(image,channel) affine
+ *   scale = rstd*gamma*(1+ts), shift = (beta - mean*rstd*gamma)*(1+ts) + tb
+ * where (ts, tb) are the time-embedding scale/shift rows (may be NULL). partial: [B][ntile][G][2]. */
+int idiff_gn_finalize(const float* partial, int ntile, const float* gamma, const float* beta,
+                      const float* t_scale, const float* t_shift, int t_ld, float* scale_out,
+                      float* shift_out, int B, int C, int G, int count_per_group, float eps, void* stream);
+
+/* GroupNorm statistics of a bf16 NHWC tensor as partial sums [B][ntile][G][2] (ntile returned
+ * by idiff_gn_stats_ntile). */
+int idiff_gn_stats(const void* src, float* partial, int B, int HW, int C, int G, void* stream);
+int idiff_gn_stats_ntile(int HW);
+
+/* out = silu(y*scale+shift) + res  (ResBlock tail when cin == cout); optional per-pixel channel
+ * LayerNorm statistics of the result. */
+int idiff_block_tail(const void* y, const float* scale, const float* shift, const void* res, void* out,
+                     float* out_row_stats, float ln_eps, int B, int HW, int C, void* stream);
+
+/* out = a (+ b); optional row stats.  Used for cat([x + x_, x_]) and similar glue. */
+int idiff_add_rows(const void* a, const void* b, void* out, float* out_row_stats, float ln_eps, size_t rows,
+                   int C, void* stream);
+
+/* y = LayerNorm_c(x) * g  (channel LayerNorm, gain only) materialised in bf16. */
+int idiff_chan_ln(const void* x, const float* g, void* y, float eps, size_t rows, int C, void* stream);
+
+/* Linear attention context.  qkv: bf16 [B][HW][384] (q already soft-maxed by the GEMM epilogue).
+ * Computes ctx[b,h,d,e] = sum_n softmax_n(k)[d,n] v[e,n] / HW, then the per-image effective output
+ * weight Weff[b] = Wout * blockdiag(ctx^T) packed for idiff_conv_gemm (NT = C). */
+int idiff_linattn_context(const void* qkv, const float* w_out /*[C][128]*/, void* weff_packed,
+                          float* scratch, int B, int HW, int C, void* stream);
+size_t idiff_linattn_scratch_floats(int B, int HW);
+
+/* Multi-head self-attention, head dim 32: qkv bf16 [B][L][3*C] (q|k|v, heads contiguous), out bf16
+ * [B][L][C].  tcgen05 QK^T and PV with fp32 softmax. */
+int idiff_self_attention(const void* qkv, void* out, int B, int L, int heads, float scale, void* stream);
+
+/* fp32 <-> bf16 / layout helpers */
+int idiff_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
+int idiff_bf16_to_f32(const void* src, float* dst, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDIFF_H_ */

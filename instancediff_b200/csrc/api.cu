@@ -1,0 +1,44 @@
+// Error plumbing + watchdog word shared by every kernel file of libidiff_sm100.so.
+#include "host_common.h"
+
+namespace idiff {
+__device__ int g_watchdog = 0;
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return IDIFF_OK;
+}
+}  // namespace idiff
+
+extern "C" {
+
+int idiff_abi_version(void) { return 1; }
+
+int idiff_sizeof_gemm_params(void) { return (int)sizeof(idiff_gemm_params); }
+
+const char* idiff_last_error(void) { return idiff::g_err; }
+
+int idiff_watchdog_status(int clear) {
+  int v = 0;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return idiff::fail(IDIFF_ERR_CUDA, "watchdog sync: %s", cudaGetErrorString(e));
+  e = cudaMemcpyFromSymbol(&v, idiff::g_watchdog, sizeof(int));
+  if (e != cudaSuccess) return idiff::fail(IDIFF_ERR_CUDA, "watchdog read: %s", cudaGetErrorString(e));
+  if (clear && v != 0) {
+    int z = 0;
+    cudaMemcpyToSymbol(idiff::g_watchdog, &z, sizeof(int));
+  }
+  if (v != 0) idiff::fail(IDIFF_ERR_WATCHDOG, "device pipeline wait timed out at site %d", v);
+  return v;
+}
+
+}  // extern "C"

@@ -1,0 +1,374 @@
+// Attention kernels of the UNet:
+//  * self-attention of the SpatialTransformer (head dim 32): S = Q K^T and O = P V on tcgen05 with the
+//    accumulators in TMEM, fp32 online softmax in registers, P re-staged through shared memory in the
+//    UMMA K-major layout, V consumed as an MN-major operand (no transpose pass).
+//  * linear attention (levels 0-2): k-softmax over pixels folded into a streaming context reduction
+//    ctx[d][e] = sum_n softmax_n(k)[d,n] v[e,n] / HW, then the per-image effective output weight
+//    Weff = Wout * blockdiag(ctx^T) written directly in the packed layout the GEMM engine streams.
+// Serves `self.model(x, self.mu, t*scale, **kwargs)`, utils/sde_utils.py:198.
+#include "common.cuh"
+#include "host_common.h"
+
+namespace idiff {
+
+// =====================================================================================================
+// Self-attention.  grid = (ceil(L/128), heads, B), block = 128 threads (thread r owns query row r).
+// =====================================================================================================
+constexpr int AT_PLANE = 128 * 16 + 32;           // bytes between 8-element planes of a 128-row tile
+constexpr int AT_Q = 0;                           // [4 planes]  Q tile   (A of S = Q K^T, K-major)
+constexpr int AT_K = AT_Q + 4 * AT_PLANE;         // [4 planes]  K block  (B of S, K-major: keys x d)
+constexpr int AT_V = AT_K + 4 * AT_PLANE;         // [4 planes]  V block  (B of O = P V, MN-major: d x keys)
+constexpr int AT_P = AT_V + 4 * AT_PLANE;         // [16 planes] P        (A of O, K-major: rows x keys)
+constexpr int AT_BAR = AT_P + 16 * AT_PLANE;
+constexpr int AT_SMEM = AT_BAR + 64;
+
+static int g_debug_flags = 0;
+
+__global__ void __launch_bounds__(128)
+self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int L, int heads,
+                      float scale_log2e, int dbg) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  uint64_t* bar_s = reinterpret_cast<uint64_t*>(sm + AT_BAR);
+  uint64_t* bar_o = bar_s + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int C = heads * 32, ld = 3 * C;
+  const __nv_bfloat16* base = qkv + (size_t)b * L * ld + h * 32;
+
+  if (tid == 0) {
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // tile loader: 128 rows x 32 channels -> [4 planes][128 rows][8]; rows >= L are zero
+  auto load_tile = [&](int smem_off, int row0, int col_off) {
+    const int c8 = tid & 3;
+    for (int r = tid >> 2; r < 128; r += 32) {
+      uint4 q = make_uint4(0u, 0u, 0u, 0u);
+      if (row0 + r < L) q = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(row0 + r) * ld + col_off + c8 * 8));
+      *reinterpret_cast<uint4*>(sm + smem_off + c8 * AT_PLANE + r * 16) = q;
+    }
+  };
+
+  load_tile(AT_Q, q0, 0);
+
+  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);
+  const uint32_t idesc_o = umma_idesc_bf16(128, 32, 1);          // B (= V) is MN-major
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+
+  float o[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) o[e] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+
+  const int nblk = (L + 127) / 128;
+  for (int j = 0; j < nblk; ++j) {
+    const int k0 = j * 128;
+    load_tile(AT_K, k0, C);
+    load_tile(AT_V, k0, 2 * C);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const uint32_t l = (dbg & 4) ? 128 : AT_PLANE, s = (dbg & 4) ? AT_PLANE : 128;
+        const uint64_t ad = umma_desc(smem_u32(sm + AT_Q) + kk * 2 * AT_PLANE, l, s);
+        const uint64_t bd = umma_desc(smem_u32(sm + AT_K) + kk * 2 * AT_PLANE, l, s);
+        umma_bf16(tmem, ad, bd, idesc_s, kk);
+      }
+      umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, j & 1, 201);
+    tc_fence_after();
+
+    // ---- online softmax over this key block (scores scaled by 1/sqrt(d), in log2 domain) ----
+    float mx = -INFINITY;
+    for (int cc = 0; cc < 4; ++cc) {
+      float v[32];
+      tmem_ld32(lane_addr + cc * 32, v);
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        if (k0 + cc * 32 + q < L) mx = fmaxf(mx, v[q]);
+    }
+    const float m_new = fmaxf(m_run, mx * scale_log2e);
+    const float alpha = exp2f(m_run - m_new);                    // exp2f(-inf) = 0 on the first block
+    float psum = 0.f;
+    for (int cc = 0; cc < 4; ++cc) {
+      float v[32];
+      tmem_ld32(lane_addr + cc * 32, v);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const float pv = (k0 + cc * 32 + q < L) ? exp2f(fmaf(v[q], scale_log2e, -m_new)) : 0.f;
+        v[q] = pv;
+        psum += pv;
+      }
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8)
+        *reinterpret_cast<uint4*>(sm + AT_P + (cc * 4 + g8) * AT_PLANE + tid * 16) = pack_bf16x8(v + g8 * 8);
+    }
+    l_run = l_run * alpha + psum;
+    m_run = m_new;
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        // A: P planes (2kk, 2kk+1); B: V rows (keys) 16kk.. as MN-major: LBO = 8-key group pitch (128 B),
+        // SBO = pitch between 8-channel groups (plane)
+        const uint32_t l = (dbg & 4) ? 128 : AT_PLANE, s = (dbg & 4) ? AT_PLANE : 128;
+        const uint64_t ad = umma_desc(smem_u32(sm + AT_P) + kk * 2 * AT_PLANE, l, s);
+        const uint64_t bd = (dbg & 2) ? umma_desc(smem_u32(sm + AT_V) + kk * 256, AT_PLANE, 128)
+                                      : umma_desc(smem_u32(sm + AT_V) + kk * 256, 128, AT_PLANE);
+        umma_bf16(tmem, ad, bd, idesc_o, kk);
+      }
+      umma_commit(bar_o);
+    }
+    mbar_wait(bar_o, j & 1, 202);
+    tc_fence_after();
+    {
+      float v[32];
+      tmem_ld32(lane_addr, v);
+#pragma unroll
+      for (int e = 0; e < 32; ++e) o[e] = fmaf(o[e], alpha, v[e]);
+    }
+    tc_fence_before();
+    __syncthreads();      // K/V/P smem and the TMEM columns are re-used by the next block
+  }
+
+  if (q0 + tid < L) {
+    const float inv = 1.f / l_run;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) o[e] *= inv;
+    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * L + q0 + tid) * C + h * 32);
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) dst[q4] = pack_bf16x8(o + q4 * 8);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+// =====================================================================================================
+// Linear attention context.
+// =====================================================================================================
+constexpr int LA_ROWS = 256;                 // rows staged per pass
+constexpr int LA_CHUNK = 4096;               // rows per CTA
+constexpr int LA_PART = 32 + 32 + 1024;      // floats per partial: m[32], S[32], ctx[32][32]
+
+// grid = (nchunk, 4 heads, B), block = 256
+__global__ void __launch_bounds__(256)
+linattn_partial_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ part, int HW) {
+  extern __shared__ __align__(16) float lsm[];
+  float* ks = lsm;                          // [LA_ROWS][32]
+  float* vs = lsm + LA_ROWS * 32;           // [LA_ROWS][32]
+  float* red = vs + LA_ROWS * 32;           // [8][32]
+  float* mcur = red + 256;                  // [32]
+  float* fac = mcur + 32;                   // [32] rescale factor of the running sums
+  const int tid = threadIdx.x, chunk = blockIdx.x, h = blockIdx.y, b = blockIdx.z, nchunk = gridDim.x;
+  const int row_begin = chunk * LA_CHUNK, row_end = min(HW, row_begin + LA_CHUNK);
+  const __nv_bfloat16* kb = qkv + (size_t)b * HW * 384 + 128 + h * 32;
+  const __nv_bfloat16* vb = kb + 128;
+
+  const int sub = tid >> 6, tt = tid & 63, d0 = (tt >> 3) * 4, e0 = (tt & 7) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int jx = 0; jx < 4; ++jx) acc[i][jx] = 0.f;
+  float s_run = 0.f;                         // thread tid<32 keeps S[d = tid]
+  if (tid < 32) mcur[tid] = -INFINITY;
+  __syncthreads();
+
+  for (int r0 = row_begin; r0 < row_end; r0 += LA_ROWS) {
+    const int nr = min(LA_ROWS, row_end - r0);
+    // stage k and v rows as fp32 (rows beyond nr: k = -inf so exp() = 0, v = 0)
+    for (int i = tid; i < LA_ROWS * 4; i += 256) {
+      const int r = i >> 2, c8 = i & 3;
+      float fk[8], fv[8];
+      if (r < nr) {
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(kb + (size_t)(r0 + r) * 384 + c8 * 8)), fk);
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(vb + (size_t)(r0 + r) * 384 + c8 * 8)), fv);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { fk[e] = -INFINITY; fv[e] = 0.f; }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { ks[r * 32 + c8 * 8 + e] = fk[e]; vs[r * 32 + c8 * 8 + e] = fv[e]; }
+    }
+    __syncthreads();
+    // column max of this pass
+    {
+      const int d = tid & 31, rg = tid >> 5;
+      float mx = -INFINITY;
+      for (int r = rg; r < LA_ROWS; r += 8) mx = fmaxf(mx, ks[r * 32 + d]);
+      red[rg * 32 + d] = mx;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      float mx = red[tid];
+#pragma unroll
+      for (int g = 1; g < 8; ++g) mx = fmaxf(mx, red[g * 32 + tid]);
+      const float m_old = mcur[tid], m_new = fmaxf(m_old, mx);
+      fac[tid] = __expf(m_old - m_new);      // 0 on the first pass
+      mcur[tid] = m_new;
+    }
+    __syncthreads();
+    // exponentiate in place, column sums
+    {
+      const int d = tid & 31, rg = tid >> 5;
+      const float m = mcur[d];
+      float s = 0.f;
+      for (int r = rg; r < LA_ROWS; r += 8) {
+        const float ev = __expf(ks[r * 32 + d] - m);
+        ks[r * 32 + d] = ev;
+        s += ev;
+      }
+      red[rg * 32 + d] = s;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) s += red[g * 32 + tid];
+      s_run = s_run * fac[tid] + s;
+    }
+    // rescale the running context, then accumulate this pass (each 64-thread group owns 64 rows)
+    {
+      const float4 f4 = *reinterpret_cast<const float4*>(fac + d0);
+      const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jx = 0; jx < 4; ++jx) acc[i][jx] *= ff[i];
+      for (int r = sub * 64; r < sub * 64 + 64; ++r) {
+        const float4 k4 = *reinterpret_cast<const float4*>(ks + r * 32 + d0);
+        const float4 v4 = *reinterpret_cast<const float4*>(vs + r * 32 + e0);
+        const float kk[4] = {k4.x, k4.y, k4.z, k4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int jx = 0; jx < 4; ++jx) acc[i][jx] = fmaf(kk[i], vv[jx], acc[i][jx]);
+      }
+    }
+    __syncthreads();
+  }
+  // reduce the 4 row-subsets through shared memory (re-use ks) and emit the partial
+  float* cred = ks;                          // [4][1024]
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int jx = 0; jx < 4; ++jx) cred[sub * 1024 + (d0 + i) * 32 + e0 + jx] = acc[i][jx];
+  __syncthreads();
+  float* dst = part + (((size_t)b * 4 + h) * nchunk + chunk) * LA_PART;
+  for (int i = tid; i < 1024; i += 256) dst[64 + i] = cred[i] + cred[1024 + i] + cred[2048 + i] + cred[3072 + i];
+  if (tid < 32) {
+    dst[tid] = mcur[tid];
+    dst[32 + tid] = s_run;
+  }
+}
+
+// grid = B, block = 256: merge partials -> ctx (smem), then Weff[c][h*32+d] = sum_e Wout[c][h*32+e] ctx[h][d][e]
+__global__ void __launch_bounds__(256)
+linattn_merge_kernel(const float* __restrict__ part, int nchunk, const float* __restrict__ w_out,
+                     __nv_bfloat16* __restrict__ weff, int HW, int C) {
+  __shared__ float ctx[4 * 32 * 32];
+  __shared__ float mfin[128], sfin[128];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  if (tid < 128) {
+    const int h = tid >> 5, d = tid & 31;
+    const float* p0 = part + ((size_t)b * 4 + h) * nchunk * LA_PART;
+    float m = -INFINITY;
+    for (int c = 0; c < nchunk; ++c) m = fmaxf(m, p0[(size_t)c * LA_PART + d]);
+    float s = 0.f;
+    for (int c = 0; c < nchunk; ++c) s += p0[(size_t)c * LA_PART + 32 + d] * __expf(p0[(size_t)c * LA_PART + d] - m);
+    mfin[tid] = m;
+    sfin[tid] = s;
+  }
+  __syncthreads();
+  for (int i = tid; i < 4096; i += 256) {
+    const int h = i >> 10, d = (i >> 5) & 31;
+    const float* p0 = part + ((size_t)b * 4 + h) * nchunk * LA_PART;
+    const float m = mfin[h * 32 + d];
+    float a = 0.f;
+    for (int c = 0; c < nchunk; ++c)
+      a += p0[(size_t)c * LA_PART + 64 + (i & 1023)] * __expf(p0[(size_t)c * LA_PART + d] - m);
+    ctx[i] = a / (sfin[h * 32 + d] * (float)HW);           // softmax normaliser and v / (h*w)
+  }
+  __syncthreads();
+  __nv_bfloat16* wdst = weff + (size_t)b * C * 128;
+  for (int i = tid; i < C * 128; i += 256) {
+    const int c = i >> 7, kc = i & 127, h = kc >> 5, d = kc & 31;
+    const float* wr = w_out + (size_t)c * 128 + h * 32;
+    const float* cr = ctx + (h * 32 + d) * 32;
+    float a = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < 32; ++e) a = fmaf(wr[e], cr[e], a);
+    // packed B-operand layout of conv_gemm (NT = C, two 64-wide K stages)
+    const int ks = kc >> 6, kin = kc & 63;
+    wdst[(size_t)ks * C * 64 + (kin >> 3) * (C * 8) + c * 8 + (kin & 7)] = __float2bfloat16_rn(a);
+  }
+}
+
+}  // namespace idiff
+
+extern "C" {
+using namespace idiff;
+
+int idiff_self_attention(const void* qkv, void* out, int B, int L, int heads, float scale, void* stream) {
+  IDIFF_REQUIRE(qkv && out && B > 0 && L > 0 && heads > 0, "self_attention: bad arguments");
+  IDIFF_REQUIRE(aligned16(qkv) && aligned16(out), "self_attention: 16 B alignment");
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(self_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "self_attention attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  dim3 grid((unsigned)((L + 127) / 128), (unsigned)heads, (unsigned)B);
+  self_attention_kernel<<<grid, 128, AT_SMEM, as_stream(stream)>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, L,
+                                                                   heads, scale * 1.4426950408889634f, g_debug_flags);
+  return check_launch("self_attention");
+}
+
+int idiff_set_debug_flags(int flags) {
+  g_debug_flags = flags;
+  return IDIFF_OK;
+}
+
+size_t idiff_linattn_scratch_floats(int B, int HW) {
+  const size_t nchunk = (size_t)(HW + LA_CHUNK - 1) / LA_CHUNK;
+  return (size_t)B * 4 * nchunk * LA_PART;
+}
+
+int idiff_linattn_context(const void* qkv, const float* w_out, void* weff_packed, float* scratch, int B, int HW,
+                          int C, void* stream) {
+  IDIFF_REQUIRE(qkv && w_out && weff_packed && scratch && B > 0 && HW > 0, "linattn_context: bad arguments");
+  IDIFF_REQUIRE(C == 64 || C == 128 || C == 256, "linattn_context: C must be 64/128/256");
+  const int nchunk = (HW + LA_CHUNK - 1) / LA_CHUNK;
+  const int smem = (2 * LA_ROWS * 32 + 256 + 64) * (int)sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(linattn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "linattn attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  dim3 grid((unsigned)nchunk, 4u, (unsigned)B);
+  linattn_partial_kernel<<<grid, 256, smem, as_stream(stream)>>>((const __nv_bfloat16*)qkv, scratch, HW);
+  if (int rc = check_launch("linattn_partial")) return rc;
+  linattn_merge_kernel<<<B, 256, 0, as_stream(stream)>>>(scratch, nchunk, w_out, (__nv_bfloat16*)weff_packed, HW, C);
+  return check_launch("linattn_merge");
+}
+
+}  // extern "C"

@@ -1,0 +1,300 @@
+// HBM-bound glue kernels of the UNet forward: GroupNorm statistics/finalize, ResBlock tail,
+// channel LayerNorm, row adds, dtype conversion, time embedding.  All are vectorised (16 B per
+// thread = 8 bf16 channels), coalesced along the channel-last axis, warp-shuffle reductions.
+// Spec: SURVEY.md App. A (ResBlock / PreNorm / time MLP); serves utils/sde_utils.py:198.
+#include "common.cuh"
+#include "host_common.h"
+
+namespace idiff {
+
+static inline int blocks_for(size_t items, int block, int cap = 148 * 16) {
+  size_t g = (items + block - 1) / block;
+  if (g > (size_t)cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+
+// ---- dtype conversion ----------------------------------------------------------------------------
+__global__ void f32_to_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) d[i] = __float2bfloat16_rn(s[i]);
+}
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ d, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) d[i] = __bfloat162float(s[i]);
+}
+
+// Reduce (s1, s2) over the `lanes_per_row` consecutive lanes that share a row (power of two <= 32).
+IDIFF_DEVINL void row_reduce(float& s1, float& s2, int lanes_per_row) {
+  for (int o = lanes_per_row >> 1; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+}
+
+// ---- ResBlock tail: out = silu(y*scale+shift) + res ; optional LayerNorm row statistics ----------
+// rows = B*HW, C in {64,128,256}; thread = one 8-channel vector.
+template <int MODE>   // 0: block tail, 1: a (+ b), 2: channel LayerNorm apply
+__global__ void __launch_bounds__(256)
+rowwise_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b2,
+               const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ gain,
+               __nv_bfloat16* __restrict__ out, float* __restrict__ row_stats, float eps, size_t rows, int HW, int C) {
+  const int lpr = C >> 3;                                   // lanes per row
+  const size_t nvec = rows * lpr;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x; i0 < nvec; i0 += stride) {
+    const size_t i = i0 + threadIdx.x;
+    const bool act = i < nvec;
+    const size_t row = act ? i / lpr : 0;
+    const int c0 = act ? (int)(i - row * lpr) * 8 : 0;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = 0.f;
+    if (act) {
+      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(a + row * C + c0)), f);
+      if (MODE == 0) {
+        const size_t img = row / HW;
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + img * C + c0));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + img * C + c0 + 4));
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(shift + img * C + c0));
+        const float4 t1 = __ldg(reinterpret_cast<const float4*>(shift + img * C + c0 + 4));
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = silu_fast(fmaf(f[e], sc[e], sh[e]));
+      }
+      if (MODE != 2 && b2) {
+        float r[8];
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(b2 + row * C + c0)), r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += r[e];
+      }
+    }
+    if (MODE == 2 || row_stats) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s1 += f[e]; s2 += f[e] * f[e]; }
+      row_reduce(s1, s2, lpr);
+      const float mean = s1 / C, var = fmaxf(s2 / C - mean * mean, 0.f), rstd = rsqrtf(var + eps);
+      if (MODE == 2) {
+        if (act) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gain + c0));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gain + c0 + 4));
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = (f[e] - mean) * rstd * gg[e];
+        }
+      } else if (act && c0 == 0) {
+        row_stats[2 * row] = mean;
+        row_stats[2 * row + 1] = rstd;
+      }
+    }
+    if (act) *reinterpret_cast<uint4*>(out + row * C + c0) = pack_bf16x8(f);
+  }
+}
+
+// ---- GroupNorm statistics of a bf16 [B][HW][C] tensor -> partial[(b*ntile+tile)*G+g][2] -----------
+constexpr int GN_TILE_ROWS = 128;
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ partial, int HW, int C, int G) {
+  __shared__ float red[256][2];
+  const int b = blockIdx.y, tile = blockIdx.x, ntile = gridDim.x;
+  const int lpr = C >> 3, rows_per_sweep = 256 / lpr;
+  const int c8 = threadIdx.x % lpr, roff = threadIdx.x / lpr;
+  const int r_end = min(HW, (tile + 1) * GN_TILE_ROWS);
+  float s1 = 0.f, s2 = 0.f;
+  for (int r = tile * GN_TILE_ROWS + roff; r < r_end; r += rows_per_sweep) {
+    float f[8];
+    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(src + ((size_t)b * HW + r) * C + c8 * 8)), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s1 += f[e]; s2 += f[e] * f[e]; }
+  }
+  red[threadIdx.x][0] = s1;
+  red[threadIdx.x][1] = s2;
+  __syncthreads();
+  const int cpg = C / G, vpg = cpg >> 3;                     // 8-channel vectors per group
+  if (threadIdx.x < G) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int ro = 0; ro < rows_per_sweep; ++ro)
+      for (int v = 0; v < vpg; ++v) {
+        const int t = ro * lpr + threadIdx.x * vpg + v;
+        a1 += red[t][0];
+        a2 += red[t][1];
+      }
+    float* dst = partial + (((size_t)b * ntile + tile) * G + threadIdx.x) * 2;
+    dst[0] = a1;
+    dst[1] = a2;
+  }
+}
+
+// ---- GroupNorm finalize: partial sums -> per-(image,channel) affine (with time modulation) -------
+// grid = B, block = 32*G threads (one warp per group reduces the tiles in a fixed order).
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int ntile, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ t_scale,
+                                   const float* __restrict__ t_shift, int t_ld, float* __restrict__ scale_out,
+                                   float* __restrict__ shift_out, int C, int G, float inv_count, float eps) {
+  __shared__ float stat[64][2];
+  const int b = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float s1 = 0.f, s2 = 0.f;
+  for (int t = lane; t < ntile; t += 32) {
+    const float* src = partial + (((size_t)b * ntile + t) * G + g) * 2;
+    s1 += src[0];
+    s2 += src[1];
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    const float mean = s1 * inv_count;
+    const float var = fmaxf(s2 * inv_count - mean * mean, 0.f);
+    stat[g][0] = mean;
+    stat[g][1] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = stat[c / cpg][0], rstd = stat[c / cpg][1];
+    float sc = rstd * gamma[c];
+    float sh = beta[c] - mean * sc;
+    if (t_scale) {
+      const float ts = 1.f + t_scale[(size_t)b * t_ld + c];
+      sc *= ts;
+      sh = fmaf(sh, ts, t_shift[(size_t)b * t_ld + c]);
+    }
+    scale_out[(size_t)b * C + c] = sc;
+    shift_out[(size_t)b * C + c] = sh;
+  }
+}
+
+// ---- time embedding ---------------------------------------------------------------------------
+// grid = B, block = 4*nf threads.  temb_act[b][j] = silu( W2 gelu(W1 sincos(t_b) + b1) + b2 )[j]
+__global__ void time_mlp_kernel(const float* __restrict__ t, float t_scalar, const float* __restrict__ w1,
+                                const float* __restrict__ b1, const float* __restrict__ w2,
+                                const float* __restrict__ b2, float* __restrict__ temb_act, int nf) {
+  extern __shared__ float sh[];
+  float* pos = sh;              // [nf]
+  float* h1 = sh + nf;          // [4nf]
+  const int b = blockIdx.x, j = threadIdx.x, td = 4 * nf, half = nf >> 1;
+  const float tv = t ? t[b] : t_scalar;
+  if (j < nf) {
+    const int i = j < half ? j : j - half;
+    const float freq = expf((float)i * (-logf(10000.0f) / (float)(half - 1)));
+    const float arg = tv * freq;
+    pos[j] = j < half ? sinf(arg) : cosf(arg);
+  }
+  __syncthreads();
+  float acc = b1[j];
+  for (int k = 0; k < nf; ++k) acc = fmaf(w1[(size_t)k * td + j], pos[k], acc);   // w1 stored transposed [nf][4nf]
+  h1[j] = gelu_erf(acc);
+  __syncthreads();
+  float o = b2[j];
+  for (int k = 0; k < td; ++k) o = fmaf(w2[(size_t)k * td + j], h1[k], o);       // w2 stored transposed [4nf][4nf]
+  temb_act[(size_t)b * td + j] = o / (1.f + expf(-o));          // SiLU feeding every ResBlock's Linear
+}
+
+// out_ss[b][s] = wss[s][:] . temb_act[b][:] + bss[s]; one warp per output row s, loops over images.
+__global__ void __launch_bounds__(256)
+time_proj_kernel(const float* __restrict__ temb_act, const float* __restrict__ wss, const float* __restrict__ bss,
+                 float* __restrict__ out_ss, int B, int td, int S) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= S) return;
+  float w[8];
+  const int per_lane = td / 32;                              // td = 256 -> 8
+  for (int q = 0; q < per_lane; ++q) w[q] = wss[(size_t)warp * td + q * 32 + lane];
+  for (int b = 0; b < B; ++b) {
+    float acc = 0.f;
+    for (int q = 0; q < per_lane; ++q) acc = fmaf(w[q], temb_act[(size_t)b * td + q * 32 + lane], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out_ss[(size_t)b * S + warp] = acc + bss[warp];
+  }
+}
+
+}  // namespace idiff
+
+extern "C" {
+using namespace idiff;
+
+int idiff_f32_to_bf16(const float* src, void* dst, size_t n, void* stream) {
+  IDIFF_REQUIRE(src && dst, "f32_to_bf16: null");
+  if (!n) return IDIFF_OK;
+  f32_to_bf16_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, n);
+  return check_launch("f32_to_bf16");
+}
+int idiff_bf16_to_f32(const void* src, float* dst, size_t n, void* stream) {
+  IDIFF_REQUIRE(src && dst, "bf16_to_f32: null");
+  if (!n) return IDIFF_OK;
+  bf16_to_f32_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, dst, n);
+  return check_launch("bf16_to_f32");
+}
+
+static int check_c(int C, const char* who) {
+  IDIFF_REQUIRE(C == 64 || C == 128 || C == 256, "%s: C must be 64/128/256 (got %d)", who, C);
+  return IDIFF_OK;
+}
+
+int idiff_block_tail(const void* y, const float* scale, const float* shift, const void* res, void* out,
+                     float* out_row_stats, float ln_eps, int B, int HW, int C, void* stream) {
+  IDIFF_REQUIRE(y && scale && shift && out && B > 0 && HW > 0, "block_tail: bad arguments");
+  if (int rc = check_c(C, "block_tail")) return rc;
+  const size_t rows = (size_t)B * HW;
+  rowwise_kernel<0><<<blocks_for(rows * (C / 8), 256), 256, 0, as_stream(stream)>>>(
+      (const __nv_bfloat16*)y, (const __nv_bfloat16*)res, scale, shift, nullptr, (__nv_bfloat16*)out, out_row_stats,
+      ln_eps, rows, HW, C);
+  return check_launch("block_tail");
+}
+
+int idiff_add_rows(const void* a, const void* b, void* out, float* out_row_stats, float ln_eps, size_t rows, int C,
+                   void* stream) {
+  IDIFF_REQUIRE(a && out && rows > 0, "add_rows: bad arguments");
+  if (int rc = check_c(C, "add_rows")) return rc;
+  rowwise_kernel<1><<<blocks_for(rows * (C / 8), 256), 256, 0, as_stream(stream)>>>(
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nullptr, nullptr, nullptr, (__nv_bfloat16*)out, out_row_stats,
+      ln_eps, rows, 1, C);
+  return check_launch("add_rows");
+}
+
+int idiff_chan_ln(const void* x, const float* g, void* y, float eps, size_t rows, int C, void* stream) {
+  IDIFF_REQUIRE(x && g && y && rows > 0, "chan_ln: bad arguments");
+  if (int rc = check_c(C, "chan_ln")) return rc;
+  rowwise_kernel<2><<<blocks_for(rows * (C / 8), 256), 256, 0, as_stream(stream)>>>(
+      (const __nv_bfloat16*)x, nullptr, nullptr, nullptr, g, (__nv_bfloat16*)y, nullptr, eps, rows, 1, C);
+  return check_launch("chan_ln");
+}
+
+int idiff_gn_stats_ntile(int HW) { return (HW + GN_TILE_ROWS - 1) / GN_TILE_ROWS; }
+
+int idiff_gn_stats(const void* src, float* partial, int B, int HW, int C, int G, void* stream) {
+  IDIFF_REQUIRE(src && partial && B > 0 && HW > 0, "gn_stats: bad arguments");
+  if (int rc = check_c(C, "gn_stats")) return rc;
+  IDIFF_REQUIRE(G > 0 && C % G == 0 && (C / G) % 8 == 0 && G <= 256, "gn_stats: unsupported groups %d", G);
+  dim3 grid((unsigned)idiff_gn_stats_ntile(HW), (unsigned)B);
+  gn_stats_kernel<<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)src, partial, HW, C, G);
+  return check_launch("gn_stats");
+}
+
+int idiff_gn_finalize(const float* partial, int ntile, const float* gamma, const float* beta, const float* t_scale,
+                      const float* t_shift, int t_ld, float* scale_out, float* shift_out, int B, int C, int G,
+                      int count_per_group, float eps, void* stream) {
+  IDIFF_REQUIRE(partial && gamma && beta && scale_out && shift_out, "gn_finalize: null pointer");
+  IDIFF_REQUIRE(B > 0 && ntile > 0 && G > 0 && G <= 32 && C % G == 0 && count_per_group > 0, "gn_finalize: bad sizes");
+  IDIFF_REQUIRE((t_scale == nullptr) == (t_shift == nullptr), "gn_finalize: t_scale/t_shift must come together");
+  gn_finalize_kernel<<<B, 32 * G, 0, as_stream(stream)>>>(partial, ntile, gamma, beta, t_scale, t_shift, t_ld,
+                                                          scale_out, shift_out, C, G, 1.0f / (float)count_per_group,
+                                                          eps);
+  return check_launch("gn_finalize");
+}
+
+int idiff_time_embed(const float* t, float t_scalar, const float* w1, const float* b1, const float* w2,
+                     const float* b2, const float* wss, const float* bss, float* temb_scratch, float* out_ss, int B,
+                     int nf, int S, void* stream) {
+  IDIFF_REQUIRE(w1 && b1 && w2 && b2 && wss && bss && temb_scratch && out_ss, "time_embed: null pointer");
+  IDIFF_REQUIRE(B > 0 && S > 0 && nf >= 8 && nf % 8 == 0 && 4 * nf <= 1024 && (4 * nf) % 32 == 0 && 4 * nf / 32 <= 8,
+                "time_embed: unsupported nf %d", nf);
+  const int td = 4 * nf;
+  time_mlp_kernel<<<B, td, (nf + td) * sizeof(float), as_stream(stream)>>>(t, t_scalar, w1, b1, w2, b2, temb_scratch, nf);
+  if (int rc = check_launch("time_mlp")) return rc;
+  const int warps_per_block = 8;
+  time_proj_kernel<<<(S + warps_per_block - 1) / warps_per_block, 256, 0, as_stream(stream)>>>(temb_scratch, wss, bss,
+                                                                                              out_ss, B, td, S);
+  return check_launch("time_proj");
+}
+
+}  // extern "C"

@@ -1,0 +1,228 @@
+// Fused reverse-SDE Euler-Maruyama update (HBM-bound, one pass).
+//
+// Replaces utils/sde_utils.py:187-188 (score from noise), :178-179 (reverse drift), :184-185
+// (dispersion) and :45-46 (x - drift - dispersion): 12 ATen launches / ~108 B per element in the
+// reference, 20 B per element here with pre-drawn z (read x, eps, mu, z; write x) and 16 B with
+// the in-kernel Philox draw.  Arithmetic keeps the reference's fp32 operation ORDER with explicit
+// round-to-nearest intrinsics (no FMA contraction) so the result matches the CPU oracle bit for bit.
+#include "common.cuh"
+#include "host_common.h"
+
+namespace idiff {
+
+// ---- Philox4x32-10 ----------------------------------------------------------------------------
+struct Philox {
+  static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  IDIFF_DEVINL static uint4 gen(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+      const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+      ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+      key.x += W0;
+      key.y += W1;
+    }
+    return ctr;
+  }
+};
+
+// 4 standard normals for the 4-element group `grp` of stream (seed, step).
+IDIFF_DEVINL float4 philox_normal4(uint64_t seed, uint64_t grp, uint32_t step) {
+  const uint4 r = Philox::gen(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), step, 0u),
+                              make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = fmaf((float)r.x, k, 0.5f * k), u1 = fmaf((float)r.y, k, 0.5f * k);
+  const float u2 = fmaf((float)r.z, k, 0.5f * k), u3 = fmaf((float)r.w, k, 0.5f * k);
+  const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
+  float s0, c0, s1, c1;
+  __sincosf(6.283185307179586f * u1, &s0, &c0);
+  __sincosf(6.283185307179586f * u3, &s1, &c1);
+  return make_float4(ra * c0, ra * s0, rb * c1, rb * s1);
+}
+
+struct StepCoef {
+  float theta, sigma, sbar, dt, sqrt_dt;
+  uint32_t step;
+};
+
+IDIFF_DEVINL float sde_update(float x, float e, float mu, float z, const StepCoef& c, bool is_score, bool has_noise) {
+  // utils/sde_utils.py:188   score = -noise / sigma_bar
+  const float score = is_score ? e : __fdiv_rn(-e, c.sbar);
+  // :179   (theta*(mu - x) - sigma**2 * score) * dt
+  const float t1 = __fmul_rn(c.theta, __fsub_rn(mu, x));
+  const float t2 = __fmul_rn(__fmul_rn(c.sigma, c.sigma), score);
+  const float drift = __fmul_rn(__fsub_rn(t1, t2), c.dt);
+  float out = __fsub_rn(x, drift);                       // :42 / :46 left-associated
+  if (has_noise) {
+    // :185   sigma * (randn * sqrt(dt))
+    const float disp = __fmul_rn(c.sigma, __fmul_rn(z, c.sqrt_dt));
+    out = __fsub_rn(out, disp);
+  }
+  return out;
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(256)
+sde_step_kernel(float* __restrict__ xo, const float* __restrict__ x, const float* __restrict__ eps,
+                const float* __restrict__ mu, const float* __restrict__ z, const float* __restrict__ coef,
+                int is_score, int philox, uint64_t seed, uint64_t elem_offset, size_t n) {
+  StepCoef c;
+  c.theta = __ldg(coef + 0);
+  c.sigma = __ldg(coef + 1);
+  c.sbar = __ldg(coef + 2);
+  c.dt = __ldg(coef + 3);
+  c.sqrt_dt = __ldg(coef + 4);
+  c.step = __float_as_uint(__ldg(coef + 5));
+  const bool noise = philox || z != nullptr;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (kVec) {
+    const size_t n4 = n >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 xv = __ldcs(reinterpret_cast<const float4*>(x) + i);
+      const float4 ev = __ldcs(reinterpret_cast<const float4*>(eps) + i);
+      const float4 mv = mu ? __ldg(reinterpret_cast<const float4*>(mu) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (philox) zv = philox_normal4(seed, (elem_offset >> 2) + i, c.step);
+      else if (z) zv = __ldcs(reinterpret_cast<const float4*>(z) + i);
+      float4 o;
+      o.x = sde_update(xv.x, ev.x, mv.x, zv.x, c, is_score, noise);
+      o.y = sde_update(xv.y, ev.y, mv.y, zv.y, c, is_score, noise);
+      o.z = sde_update(xv.z, ev.z, mv.z, zv.z, c, is_score, noise);
+      o.w = sde_update(xv.w, ev.w, mv.w, zv.w, c, is_score, noise);
+      reinterpret_cast<float4*>(xo)[i] = o;
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      float zv = 0.f;
+      if (philox) {
+        const uint64_t g = elem_offset + i;
+        const float4 q = philox_normal4(seed, g >> 2, c.step);
+        const int l = (int)(g & 3);
+        zv = l == 0 ? q.x : l == 1 ? q.y : l == 2 ? q.z : q.w;
+      } else if (z) {
+        zv = z[i];
+      }
+      xo[i] = sde_update(x[i], eps[i], mu ? mu[i] : 0.f, zv, c, is_score, noise);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+noise_state_kernel(float* __restrict__ xo, const float* __restrict__ mu, const float* __restrict__ z,
+                   float max_sigma, int philox, uint64_t seed, uint64_t elem_offset, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float zv;
+    if (philox) {
+      const uint64_t g = elem_offset + i;
+      const float4 q = philox_normal4(seed, g >> 2, 0xFFFFFFFFu);   // step word reserved for x_T
+      const int l = (int)(g & 3);
+      zv = l == 0 ? q.x : l == 1 ? q.y : l == 2 ? q.z : q.w;
+    } else {
+      zv = z[i];
+    }
+    // utils/sde_utils.py:341   tensor + randn * max_sigma
+    xo[i] = __fadd_rn(mu[i], __fmul_rn(zv, max_sigma));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+philox_normal_kernel(float* __restrict__ out, uint64_t seed, uint64_t elem_offset, uint32_t step, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t g = elem_offset + i;
+    const float4 q = philox_normal4(seed, g >> 2, step);
+    const int l = (int)(g & 3);
+    out[i] = l == 0 ? q.x : l == 1 ? q.y : l == 2 ? q.z : q.w;
+  }
+}
+
+// Select the coefficient row for the step held in *t_counter, publish the model time, decrement.
+// Lets one captured CUDA graph serve every step of utils/sde_utils.py:248.
+__global__ void step_select_kernel(const float* __restrict__ table, int* __restrict__ t_counter,
+                                   float* __restrict__ cur_row, float* __restrict__ cur_time, float sample_scale) {
+  const int t = *t_counter;
+  if (threadIdx.x < 8) cur_row[threadIdx.x] = table[(size_t)t * 8 + threadIdx.x];
+  if (threadIdx.x == 8) *cur_time = (float)t * sample_scale;       // :198   t * scale
+  __syncthreads();
+  if (threadIdx.x == 0) *t_counter = t - 1;
+}
+
+static int grid_for(size_t work_items, int block) {
+  size_t g = (work_items + block - 1) / block;
+  const size_t cap = 148 * 8;                 // 8 resident 256-thread CTAs per SM, grid-stride beyond
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace idiff
+
+extern "C" {
+
+int idiff_sde_step(float* x_out, const float* x, const float* eps, const float* mu, const float* z,
+                   const float* coef, int input_is_score, int use_philox, uint64_t seed, uint64_t elem_offset,
+                   size_t n, void* stream) {
+  using namespace idiff;
+  IDIFF_REQUIRE(x_out && x && eps && coef, "sde_step: null pointer");
+  if (n == 0) return IDIFF_OK;
+  const bool vec = (n % 4 == 0) && aligned16(x_out) && aligned16(x) && aligned16(eps) && (!mu || aligned16(mu)) &&
+                   (!z || aligned16(z)) && (elem_offset % 4 == 0);
+  if (vec) {
+    sde_step_kernel<true><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
+        x_out, x, eps, mu, z, coef, input_is_score, use_philox, seed, elem_offset, n);
+  } else {
+    sde_step_kernel<false><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+        x_out, x, eps, mu, z, coef, input_is_score, use_philox, seed, elem_offset, n);
+  }
+  return check_launch("sde_step");
+}
+
+int idiff_sde_pack_table(const float* theta, const float* sigma, const float* sigma_bar, int T1, float dt,
+                         double sqrt_dt, float* out) {
+  IDIFF_REQUIRE(theta && sigma && sigma_bar && out && T1 > 0, "sde_pack_table: bad arguments");
+  for (int t = 0; t < T1; ++t) {
+    float* r = out + (size_t)t * 8;
+    r[0] = theta[t];
+    r[1] = sigma[t];
+    r[2] = sigma_bar[t];
+    r[3] = dt;
+    r[4] = (float)sqrt_dt;      // Python double -> fp32 scalar, as torch does for `randn * math.sqrt(dt)`
+    uint32_t step = (uint32_t)t;
+    float as_float;
+    static_assert(sizeof(as_float) == sizeof(step), "");
+    __builtin_memcpy(&as_float, &step, 4);
+    r[5] = as_float;
+    r[6] = 0.f;
+    r[7] = 0.f;
+  }
+  return IDIFF_OK;
+}
+
+int idiff_step_select(const float* table, int* t_counter, float* cur_row, float* cur_time, float sample_scale,
+                      void* stream) {
+  using namespace idiff;
+  IDIFF_REQUIRE(table && t_counter && cur_row && cur_time, "step_select: null pointer");
+  step_select_kernel<<<1, 32, 0, as_stream(stream)>>>(table, t_counter, cur_row, cur_time, sample_scale);
+  return check_launch("step_select");
+}
+
+int idiff_noise_state(float* x_out, const float* mu, const float* z, float max_sigma, int use_philox,
+                      uint64_t seed, uint64_t elem_offset, size_t n, void* stream) {
+  using namespace idiff;
+  IDIFF_REQUIRE(x_out && mu && (z || use_philox), "noise_state: null pointer");
+  if (n == 0) return IDIFF_OK;
+  noise_state_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x_out, mu, z, max_sigma, use_philox, seed,
+                                                                      elem_offset, n);
+  return check_launch("noise_state");
+}
+
+int idiff_philox_normal(float* out, uint64_t seed, uint64_t elem_offset, uint32_t step, size_t n, void* stream) {
+  using namespace idiff;
+  IDIFF_REQUIRE(out, "philox_normal: null pointer");
+  if (n == 0) return IDIFF_OK;
+  philox_normal_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(out, seed, elem_offset, step, n);
+  return check_launch("philox_normal");
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+"""Weight packing for the tcgen05 engine (host side, done once per weight load).
+
+The B operand of ``idiff_conv_gemm`` is streamed by 1-D bulk TMA, so the weights are stored in
+global memory as the exact shared-memory image of the UMMA SWIZZLE_NONE K-major layout:
+
+    packed[n_tile][chunk][tap][c8][n_local][e]      bf16
+      n_tile  = n // NT,  n_local = n % NT
+      chunk   = c // 64   (64 input channels per pipeline stage)
+      tap     = ky * k + kx
+      c8      = (c % 64) // 8,  e = c % 8           (8 channels = one 16 B core-matrix row)
+
+so one (chunk, tap) stage is ``NT * 64`` contiguous elements with LBO = NT*16 B, SBO = 128 B.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def pack_conv_weight(w: torch.Tensor, NT: int) -> torch.Tensor:
+    """w: [N, Cin, k, k] (or [N, Cin] for a linear layer) fp32 -> packed bf16 1-D tensor."""
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    N, Cin, kh, kw = w.shape
+    assert kh == kw and N % NT == 0 and Cin % 64 == 0, (w.shape, NT)
+    t = w.permute(0, 2, 3, 1).reshape(N // NT, NT, kh * kw, Cin // 64, 8, 8)
+    #            n_tile, n_local, tap, chunk, c8, e  ->  n_tile, chunk, tap, c8, n_local, e
+    t = t.permute(0, 3, 2, 4, 1, 5).contiguous()
+    return t.to(torch.bfloat16).reshape(-1)
+
+
+def unpack_conv_weight(p: torch.Tensor, N: int, Cin: int, k: int, NT: int) -> torch.Tensor:
+    """Inverse of pack_conv_weight (tests)."""
+    t = p.reshape(N // NT, Cin // 64, k * k, 8, NT, 8).permute(0, 4, 2, 1, 3, 5)
+    return t.reshape(N, k, k, Cin).permute(0, 3, 1, 2).float()
+
+
+def bf16_round(w: torch.Tensor) -> torch.Tensor:
+    return w.to(torch.bfloat16).float()
+
+
+def fold_layernorm(w: torch.Tensor, gain: torch.Tensor, beta: torch.Tensor | None):
+    """LayerNorm folded into the following linear layer.
+
+    y = W (g * (x - m) * r + beta)  =  r * (W' x - m * wsum) + W beta,   W' = W diag(g)
+    Returns (W', wsum, extra_bias) with wsum computed from the bf16-rounded W' the tensor core sees.
+    """
+    wf = w * gain[None, :]
+    wsum = bf16_round(wf).sum(dim=1)
+    extra = w @ beta if beta is not None else None
+    return wf, wsum, extra
+
+
+def interleave_geglu(w: torch.Tensor, b: torch.Tensor):
+    """[2F, K] (value rows then gate rows) -> rows interleaved (v0, g0, v1, g1, ...)."""
+    F = w.shape[0] // 2
+    wi = torch.stack([w[:F], w[F:]], dim=1).reshape(2 * F, -1)
+    bi = torch.stack([b[:F], b[F:]], dim=1).reshape(2 * F)
+    return wi, bi

@@ -1,0 +1,605 @@
+"""Drift/noise-prediction UNet on hand-written sm_100a kernels (host orchestration only).
+
+Drop-in for the network the reference plugs into ``IRSDE.set_model`` (utils/sde_utils.py:164-165)
+and calls as ``self.model(x, self.mu, t * scale, **kwargs)`` (utils/sde_utils.py:198); the wrapper
+convention ``net(a, b, t[B], names, text_encoder, image_context=A_emb)``
+(models/drift_noise_model.py:250-268) is accepted too (extra positionals are ignored).
+Architecture: SURVEY.md App. A (``models/modules/MSM_degEmb_Unet.py`` is not in the reference
+snapshot); hyper-parameters follow Configurations/config.yml:109-113.
+
+This file contains NO arithmetic on activations: it packs weights once, builds a per-shape launch
+plan (a flat list of C-ABI calls with pre-filled argument structs) and replays it.  Every kernel
+is in ``csrc/``; if ``libidiff_sm100.so`` is missing the constructor raises (no fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import EPI_GEGLU, EPI_LN_OUT, EPI_PLAIN, EPI_QSOFTMAX, GemmParams, check
+from .packing import fold_layernorm, interleave_geglu, pack_conv_weight
+
+GN_GROUPS = 8
+TILE_H, TILE_W = 16, 8
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter inventory (names == oracle/unet_oracle.py state_dict keys == the weight contract)
+# ----------------------------------------------------------------------------------------------
+def _conv(prefix, cout, cin, k, bias=True):
+    yield prefix + ".weight", (cout, cin, k, k), cin * k * k
+    if bias:
+        yield prefix + ".bias", (cout,), cin * k * k
+
+
+def _linear(prefix, cout, cin, bias=True):
+    yield prefix + ".weight", (cout, cin), cin
+    if bias:
+        yield prefix + ".bias", (cout,), cin
+
+
+def _norm(prefix, c):
+    yield prefix + ".weight", (c,), "ones"
+    yield prefix + ".bias", (c,), "zeros"
+
+
+def _resblock(prefix, cin, cout, td):
+    yield from _linear(prefix + ".mlp", 2 * cout, td)
+    yield from _conv(prefix + ".conv1", cout, cin, 3)
+    yield from _norm(prefix + ".norm1", cout)
+    yield from _conv(prefix + ".conv2", cout, cout, 3)
+    yield from _norm(prefix + ".norm2", cout)
+    if cin != cout:
+        yield from _conv(prefix + ".res_conv", cout, cin, 1)
+
+
+def _attn(prefix, dim, kind, context_dim):
+    yield prefix + ".prenorm.g", (1, dim, 1, 1), "ones"
+    f = prefix + ".fn"
+    if kind == "linear":
+        yield from _conv(f + ".to_qkv", 384, dim, 1, bias=False)
+        yield from _conv(f + ".to_out", dim, 128, 1)
+        yield f + ".out_norm.g", (1, dim, 1, 1), "ones"
+    else:
+        yield from _norm(f + ".norm", dim)
+        yield from _conv(f + ".proj_in", dim, dim, 1)
+        yield from _norm(f + ".norm1", dim)
+        for n in ("to_q", "to_k", "to_v"):
+            yield from _linear(f + ".attn1." + n, dim, dim, bias=False)
+        yield from _linear(f + ".attn1.to_out", dim, dim)
+        yield from _norm(f + ".norm2", dim)
+        yield from _linear(f + ".attn2.to_q", dim, dim, bias=False)
+        yield from _linear(f + ".attn2.to_k", dim, context_dim, bias=False)
+        yield from _linear(f + ".attn2.to_v", dim, context_dim, bias=False)
+        yield from _linear(f + ".attn2.to_out", dim, dim)
+        yield from _norm(f + ".norm3", dim)
+        yield from _linear(f + ".ff.proj", dim * 8, dim)
+        yield from _linear(f + ".ff.out", dim, dim * 4)
+        yield from _conv(f + ".proj_out", dim, dim, 1)
+
+
+def param_specs(in_nc=2, out_nc=1, nf=64, ch_mult=(1, 2, 4, 4), context_dim=512, down_kernel=4):
+    td = nf * 4
+    dims = [nf] + [nf * m for m in ch_mult]
+    io = list(zip(dims[:-1], dims[1:]))
+    n = len(io)
+    yield from _conv("init_conv", nf, in_nc, 7)
+    yield from _linear("time_lin1", td, nf)
+    yield from _linear("time_lin2", td, td)
+    for i, (di, do) in enumerate(io):
+        last = i == n - 1
+        yield from _resblock(f"downs.{i}.0", di, di, td)
+        yield from _resblock(f"downs.{i}.1", di, di, td)
+        yield from _attn(f"downs.{i}.2", di, "spatial" if last else "linear", context_dim)
+        yield from _conv(f"downs.{i}.3", do, di, 3 if last else down_kernel)
+    mid = dims[-1]
+    yield from _resblock("mid_block1", mid, mid, td)
+    yield from _attn("mid_attn", mid, "spatial", context_dim)
+    yield from _resblock("mid_block2", mid, mid, td)
+    for i, (di, do) in enumerate(reversed(io)):
+        lvl = n - 1 - i
+        yield from _resblock(f"ups.{i}.0", do + di, do, td)
+        yield from _resblock(f"ups.{i}.1", do + di, do, td)
+        yield from _attn(f"ups.{i}.2", do, "spatial" if lvl == n - 1 else "linear", context_dim)
+        yield from _conv(f"ups.{i}.3.conv" if lvl > 0 else f"ups.{i}.3", di, do, 3)
+    yield from _resblock("final_res", 2 * nf, nf, td)
+    yield from _conv("final_conv", out_nc, nf, 3)
+
+
+class _Act:
+    """A channels-last bf16 activation [B,H,W,C] (+ optional per-pixel LayerNorm stats)."""
+
+    __slots__ = ("t", "H", "W", "C", "stats")
+
+    def __init__(self, t, H, W, C, stats=None):
+        self.t, self.H, self.W, self.C, self.stats = t, H, W, C, stats
+
+
+class ConditionalUNet:
+    """``eps = net(x_t, mu, t, image_context=emb)``; fp32 [B,1,H,W] in and out, bf16 inside."""
+
+    def __init__(self, in_nc=2, out_nc=1, nf=64, ch_mult=(1, 2, 4, 4), context_dim=512, down_kernel=4,
+                 device="cuda", seed: Optional[int] = None):
+        if in_nc != 2 or out_nc != 1 or nf != 64 or tuple(ch_mult) != (1, 2, 4, 4) or down_kernel != 4:
+            raise _lib.IdiffError("ConditionalUNet: kernels are built for in_nc=2, out_nc=1, nf=64, "
+                                  "ch_mult=[1,2,4,4], down_kernel=4 (Configurations/config.yml:109-113)")
+        self.L = _lib.lib()                       # raises if the CUDA library is not built
+        self.cfg = dict(in_nc=in_nc, out_nc=out_nc, nf=nf, ch_mult=tuple(ch_mult), context_dim=context_dim,
+                        down_kernel=down_kernel)
+        self.device = torch.device(device)
+        self.nf, self.td, self.context_dim = nf, nf * 4, context_dim
+        self.dims = [nf] + [nf * m for m in ch_mult]
+        self.io = list(zip(self.dims[:-1], self.dims[1:]))
+        self.params: Dict[str, torch.Tensor] = {}
+        self._plans: Dict[tuple, "_Plan"] = {}
+        self._ctx_key = None
+        self._crossvec: Dict[tuple, torch.Tensor] = {}
+        self._init_params(seed)
+        self._pack()
+
+    # ------------------------------------------------------------------ parameters
+    def _init_params(self, seed):
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(1 if seed is None else seed)
+        for name, shape, init in param_specs(**self.cfg):
+            if init == "ones":
+                t = torch.ones(shape)
+            elif init == "zeros":
+                t = torch.zeros(shape)
+            else:                                  # nn.Conv2d / nn.Linear default: U(-1/sqrt(fan_in), +)
+                bound = 1.0 / math.sqrt(init)
+                t = (torch.rand(shape, generator=gen) * 2 - 1) * bound
+            self.params[name] = t.to(self.device, torch.float32)
+
+    def state_dict(self):
+        return {k: v.clone() for k, v in self.params.items()}
+
+    def load_state_dict(self, sd, strict=True):
+        missing = [k for k in self.params if k not in sd]
+        extra = [k for k in sd if k not in self.params]
+        if strict and (missing or extra):
+            raise KeyError(f"load_state_dict: missing {missing[:4]}..., unexpected {extra[:4]}...")
+        for k in self.params:
+            if k in sd:
+                if tuple(sd[k].shape) != tuple(self.params[k].shape):
+                    raise ValueError(f"{k}: shape {tuple(sd[k].shape)} != {tuple(self.params[k].shape)}")
+                self.params[k] = sd[k].detach().to(self.device, torch.float32).contiguous()
+        self._pack()
+        return self
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        if torch.device(device) != self.device:
+            self.device = torch.device(device)
+            self.params = {k: v.to(self.device) for k, v in self.params.items()}
+            self._pack()
+        return self
+
+    # ------------------------------------------------------------------ packing
+    def _pack(self):
+        P = self.params
+        pk: Dict[str, dict] = {}
+
+        def f32(t):
+            return t.detach().to(self.device, torch.float32).contiguous()
+
+        def conv_entry(name, NT=None, w=None, b=None, k=None):
+            w = P[name + ".weight"] if w is None else w
+            b = P.get(name + ".bias") if b is None else b
+            N = w.shape[0]
+            NT = min(N, 256) if NT is None else NT
+            pk[name] = dict(w=pack_conv_weight(w, NT).to(self.device), bias=None if b is None else f32(b), N=N, NT=NT,
+                            cin=w.shape[1], k=(w.shape[2] if w.dim() == 4 else 1) if k is None else k)
+            return pk[name]
+
+        def resblock(prefix):
+            conv_entry(prefix + ".conv1")
+            conv_entry(prefix + ".conv2")
+            if (prefix + ".res_conv.weight") in P:
+                conv_entry(prefix + ".res_conv")
+            for n in ("norm1", "norm2"):
+                pk[prefix + "." + n] = dict(g=f32(P[f"{prefix}.{n}.weight"]), b=f32(P[f"{prefix}.{n}.bias"]))
+
+        def attn(prefix, kind, dim):
+            f = prefix + ".fn"
+            g_pre = P[prefix + ".prenorm.g"].reshape(-1)
+            if kind == "linear":
+                wq = P[f + ".to_qkv.weight"].reshape(384, dim)
+                wf, wsum, _ = fold_layernorm(wq, g_pre, None)
+                e = conv_entry(f + ".to_qkv", NT=128, w=wf, b=None)
+                e["wsum"] = f32(wsum)
+                pk[f + ".to_out"] = dict(w_f32=f32(P[f + ".to_out.weight"].reshape(dim, 128)),
+                                         bias=f32(P[f + ".to_out.bias"]), g=f32(P[f + ".out_norm.g"].reshape(-1)))
+            else:
+                pk[prefix + ".prenorm"] = dict(g=f32(g_pre))
+                pk[f + ".norm"] = dict(g=f32(P[f + ".norm.weight"]), b=f32(P[f + ".norm.bias"]))
+                conv_entry(f + ".proj_in")
+                wqkv = torch.cat([P[f + ".attn1.to_q.weight"], P[f + ".attn1.to_k.weight"],
+                                  P[f + ".attn1.to_v.weight"]], dim=0)
+                wf, wsum, extra = fold_layernorm(wqkv, P[f + ".norm1.weight"], P[f + ".norm1.bias"])
+                e = conv_entry(f + ".attn1.qkv", NT=256, w=wf, b=extra)
+                e["wsum"] = f32(wsum)
+                conv_entry(f + ".attn1.to_out")
+                wi, bi = interleave_geglu(P[f + ".ff.proj.weight"], P[f + ".ff.proj.bias"])
+                wf, wsum, extra = fold_layernorm(wi, P[f + ".norm3.weight"], P[f + ".norm3.bias"])
+                e = conv_entry(f + ".ff.proj", NT=256, w=wf, b=bi + extra)
+                e["wsum"] = f32(wsum)
+                conv_entry(f + ".ff.out")
+                conv_entry(f + ".proj_out")
+
+        # stem / head / time
+        pk["init_conv"] = dict(w=f32(P["init_conv.weight"].permute(0, 2, 3, 1)), bias=f32(P["init_conv.bias"]))
+        pk["final_conv"] = dict(w=f32(P["final_conv.weight"][0].permute(1, 2, 0)),
+                                bias=float(P["final_conv.bias"].reshape(-1)[0].item()))
+        self._res_names: List[str] = []
+        n = len(self.io)
+        for i, (di, do) in enumerate(self.io):
+            kind = "spatial" if i == n - 1 else "linear"
+            for j in (0, 1):
+                resblock(f"downs.{i}.{j}")
+                self._res_names.append(f"downs.{i}.{j}")
+            attn(f"downs.{i}.2", kind, di)
+            conv_entry(f"downs.{i}.3")
+        resblock("mid_block1")
+        self._res_names.append("mid_block1")
+        attn("mid_attn", "spatial", self.dims[-1])
+        resblock("mid_block2")
+        self._res_names.append("mid_block2")
+        for i, (di, do) in enumerate(reversed(self.io)):
+            lvl = n - 1 - i
+            kind = "spatial" if lvl == n - 1 else "linear"
+            for j in (0, 1):
+                resblock(f"ups.{i}.{j}")
+                self._res_names.append(f"ups.{i}.{j}")
+            attn(f"ups.{i}.2", kind, do)
+            conv_entry(f"ups.{i}.3.conv" if lvl > 0 else f"ups.{i}.3")
+        resblock("final_res")
+        self._res_names.append("final_res")
+
+        # time embedding: transposed MLP weights + every ResBlock's Linear concatenated
+        self._ss_off: Dict[str, int] = {}
+        ws, bs, off = [], [], 0
+        for name in self._res_names:
+            w, b = P[name + ".mlp.weight"], P[name + ".mlp.bias"]
+            self._ss_off[name] = off
+            off += w.shape[0]
+            ws.append(w)
+            bs.append(b)
+        self.S = off
+        pk["time"] = dict(w1t=f32(P["time_lin1.weight"].t()), b1=f32(P["time_lin1.bias"]),
+                          w2t=f32(P["time_lin2.weight"].t()), b2=f32(P["time_lin2.bias"]),
+                          wss=f32(torch.cat(ws, 0)), bss=f32(torch.cat(bs, 0)))
+        self.pk = pk
+        self._plans.clear()
+        self._ctx_key = None
+
+    # ------------------------------------------------------------------ conditioning
+    def spatial_layers(self):
+        n = len(self.io)
+        return [f"downs.{n - 1}.2", "mid_attn", "ups.0.2"]
+
+    def set_image_context(self, ctx: torch.Tensor):
+        """Cross-attention to ONE context token: softmax == 1, so CrossAttn(x, ctx) = Wo (Wv ctx) + bo for
+        every pixel and every step (App. A) -- computed once per embedding, added as a per-image bias."""
+        if ctx.dim() == 3:
+            if ctx.shape[1] != 1:
+                raise _lib.IdiffError("image_context must hold one token per image ([B,1,D] or [B,D])")
+            ctx = ctx[:, 0]
+        key = (ctx.data_ptr(), ctx._version, tuple(ctx.shape))
+        if key == self._ctx_key:
+            return
+        c = ctx.detach().to(self.device, torch.float32)
+        B = c.shape[0]
+        for name in self.spatial_layers():
+            f = name + ".fn.attn2"
+            v = c @ self.params[f + ".to_v.weight"].t()
+            vec = v @ self.params[f + ".to_out.weight"].t() + self.params[f + ".to_out.bias"]
+            buf = self._crossvec.get((name, B))
+            if buf is None:                      # persistent per batch size: captured graphs keep the pointer
+                buf = torch.empty_like(vec)
+                self._crossvec[(name, B)] = buf
+            buf.copy_(vec)
+        self._ctx_key = key
+        for plan in self._plans.values():
+            if plan.B == B:
+                plan.bind_context(self._crossvec)
+
+    # ------------------------------------------------------------------ forward
+    def _plan(self, B, H, W, shared_time) -> "_Plan":
+        key = (B, H, W, shared_time)
+        if key not in self._plans:
+            self._plans[key] = _Plan(self, B, H, W, shared_time)
+            self._plans[key].bind_context(self._crossvec)
+        return self._plans[key]
+
+    def forward_into(self, xt, cond, time, image_context, time_ptr: Optional[int] = None):
+        """Runs the network; returns the plan-owned fp32 output buffer [B,1,H,W] (overwritten by the
+        next call).  ``time_ptr``: device float holding the shared time (CUDA-graph replay)."""
+        if xt.dtype != torch.float32 or cond.dtype != torch.float32 or not xt.is_cuda:
+            raise _lib.IdiffError("ConditionalUNet expects fp32 CUDA tensors [B,1,H,W]")
+        B, Cx, H, W = xt.shape
+        if Cx != 1 or tuple(cond.shape) != tuple(xt.shape):
+            raise _lib.IdiffError(f"expected xt and cond of shape [B,1,H,W], got {tuple(xt.shape)} / {tuple(cond.shape)}")
+        if H % 16 or W % 16:
+            raise _lib.IdiffError("H and W must be multiples of 16 (pad with ConditionalUNet.forward)")
+        if image_context is None:
+            raise _lib.IdiffError("image_context is required (use_image_context: True, config.yml:132)")
+        if image_context.shape[0] != B:
+            raise _lib.IdiffError("image_context batch does not match x")
+        self.set_image_context(image_context)
+        xt, cond = xt.contiguous(), cond.contiguous()
+        t_dev, t_scalar = None, 0.0
+        if time_ptr is not None:
+            shared = True
+        elif torch.is_tensor(time) and time.numel() > 1:
+            if time.numel() != B:
+                raise _lib.IdiffError("time tensor must have 1 or B elements")
+            shared = False
+            t_dev = time.detach().to(self.device, torch.float32).reshape(B).contiguous()
+        else:
+            shared = True
+            t_scalar = float(time.reshape(-1)[0].item()) if torch.is_tensor(time) else float(time)
+        plan = self._plan(B, H, W, shared)
+        plan.run(xt, cond, t_dev if time_ptr is None else time_ptr, t_scalar)
+        return plan.eps
+
+    def forward(self, xt, cond, time, *unused, image_context=None, **unused_kw):
+        H, W = xt.shape[-2:]
+        ph, pw = (-H) % 16, (-W) % 16
+        if ph or pw:                                 # reflect-pad right/bottom, crop after (App. A)
+            xt = torch.nn.functional.pad(xt, (0, pw, 0, ph), mode="reflect")
+            cond = torch.nn.functional.pad(cond, (0, pw, 0, ph), mode="reflect")
+        out = self.forward_into(xt, cond, time, image_context).clone()
+        return out[..., :H, :W] if (ph or pw) else out
+
+    __call__ = forward
+
+
+# ----------------------------------------------------------------------------------------------
+class _Plan:
+    """Flat launch list for one (B, H, W) shape.  Ops are closures ``f(stream_ptr)``."""
+
+    def __init__(self, net: ConditionalUNet, B, H, W, shared_time):
+        self.net, self.B, self.H, self.W, self.shared_time = net, B, H, W, shared_time
+        self.L = net.L
+        self.dev = net.device
+        self.ops: List = []
+        self.keep: List = []
+        self.scratch: Dict[tuple, torch.Tensor] = {}
+        self.ctx_slots: Dict[str, GemmParams] = {}
+        self.named: Dict[str, _Act] = {}      # block outputs by module name (layer-wise parity tests)
+        self.n_launch = 0
+        self._build()
+
+    # ---- buffers
+    def new(self, shape, dtype=torch.bfloat16):
+        t = torch.empty(shape, dtype=dtype, device=self.dev)
+        self.keep.append(t)
+        return t
+
+    def tmp(self, name, shape, dtype=torch.bfloat16):
+        key = (name, tuple(shape), dtype)
+        if key not in self.scratch:
+            self.scratch[key] = torch.empty(shape, dtype=dtype, device=self.dev)
+        return self.scratch[key]
+
+    def act(self, H, W, C, stats=False, tmp_name=None):
+        t = self.tmp(tmp_name, (self.B, H, W, C)) if tmp_name else self.new((self.B, H, W, C))
+        st = self.new((self.B * H * W, 2), torch.float32) if stats else None
+        return _Act(t, H, W, C, st)
+
+    # ---- op helpers
+    def gemm(self, src0: _Act, src1: Optional[_Act], entry: dict, out: _Act, *, k=1, stride=1, up=0,
+             a_scale=None, a_shift=None, a_silu=0, epi=EPI_PLAIN, gn_partial=None, bias=True, bias_img_slot=None,
+             row_stats=None, res0=None, res1=None, res0_scale=None, res0_shift=None, ln_g=None, out_stats=None,
+             qscale=1.0, ln_eps=1e-5, cin0=None, src0_ld=0, w_override=None, w_image_stride=0, NT=None, out_ld=None):
+        p = GemmParams()
+        p.B, p.H, p.W = self.B, out.H, out.W
+        p.ksize, p.stride, p.up0 = k, stride, up
+        p.cin0 = src0.C if cin0 is None else cin0
+        p.cin1 = src1.C if src1 is not None else 0
+        p.src0_ld, p.src1_ld = src0_ld, 0
+        p.N = entry["N"]
+        p.NT = entry["NT"] if NT is None else NT
+        p.a_silu, p.epi = a_silu, epi
+        p.gn_groups = GN_GROUPS if gn_partial is not None else 0
+        p.out_ld = out.C if out_ld is None else out_ld
+        p.src0, p.src1 = _ptr(src0.t), _ptr(src1.t if src1 is not None else None)
+        p.a_scale, p.a_shift = _ptr(a_scale), _ptr(a_shift)
+        p.w = _ptr(entry["w"] if w_override is None else w_override)
+        p.w_image_stride = w_image_stride
+        p.bias = _ptr(entry.get("bias")) if bias else None
+        p.row_stats = _ptr(row_stats)
+        p.wsum = _ptr(entry.get("wsum")) if row_stats is not None else None
+        p.res0, p.res1 = _ptr(res0), _ptr(res1)
+        p.res0_scale, p.res0_shift = _ptr(res0_scale), _ptr(res0_shift)
+        p.ln_g = _ptr(ln_g)
+        p.out = _ptr(out.t)
+        p.gn_partial = _ptr(gn_partial)
+        p.out_row_stats = _ptr(out_stats)
+        p.qscale, p.ln_eps = qscale, ln_eps
+        if bias_img_slot is not None:
+            self.ctx_slots[bias_img_slot] = p
+        self.keep.append(p)
+        L, ref = self.L, C.byref(p)
+        self.ops.append(lambda s: check(L.idiff_conv_gemm(ref, s), "conv_gemm"))
+        self.n_launch += 1
+
+    def bind_context(self, crossvec):
+        for name, p in self.ctx_slots.items():
+            buf = crossvec.get((name, self.B))
+            if buf is not None:
+                p.bias_img = buf.data_ptr()
+
+    def tiles(self, H, W):
+        return ((H + TILE_H - 1) // TILE_H) * ((W + TILE_W - 1) // TILE_W)
+
+    def gn_finalize(self, partial, ntile, norm, C, G, count, eps, t_off=None, tag="gn"):
+        sc = self.tmp(tag + "_sc", (self.B, C), torch.float32)
+        sh = self.tmp(tag + "_sh", (self.B, C), torch.float32)
+        L, B = self.L, self.B
+        if t_off is not None:
+            ts = self.ss.data_ptr() + 4 * t_off
+            tb = self.ss.data_ptr() + 4 * (t_off + C)
+            t_ld = 0 if self.shared_time else self.net.S
+        else:
+            ts = tb = None
+            t_ld = 0
+        args = (_ptr(partial), ntile, _ptr(norm["g"]), _ptr(norm["b"]), ts, tb, t_ld, _ptr(sc), _ptr(sh), B, C, G,
+                count, eps)
+        self.ops.append(lambda s: check(L.idiff_gn_finalize(*args, s), "gn_finalize"))
+        self.n_launch += 1
+        return sc, sh
+
+    def resblock(self, prefix, src0: _Act, src1: Optional[_Act], cout, want_stats=False) -> _Act:
+        pk, B, H, W = self.net.pk, self.B, src0.H, src0.W
+        cin = src0.C + (src1.C if src1 is not None else 0)
+        ntile = self.tiles(H, W)
+        count = H * W * (cout // GN_GROUPS)
+        part1 = self.tmp("gnp1", (B, ntile, GN_GROUPS, 2), torch.float32)
+        part2 = self.tmp("gnp2", (B, ntile, GN_GROUPS, 2), torch.float32)
+        y1 = self.act(H, W, cout, tmp_name="y1")
+        y2 = self.act(H, W, cout, tmp_name="y2")
+        self.gemm(src0, src1, pk[prefix + ".conv1"], y1, k=3, gn_partial=part1)
+        sc1, sh1 = self.gn_finalize(part1, ntile, pk[prefix + ".norm1"], cout, GN_GROUPS, count, 1e-5,
+                                    t_off=self.net._ss_off[prefix], tag="gn1")
+        self.gemm(y1, None, pk[prefix + ".conv2"], y2, k=3, a_scale=sc1, a_shift=sh1, a_silu=1, gn_partial=part2)
+        sc2, sh2 = self.gn_finalize(part2, ntile, pk[prefix + ".norm2"], cout, GN_GROUPS, count, 1e-5, tag="gn2")
+        out = self.act(H, W, cout, stats=want_stats)
+        if cin == cout:
+            L = self.L
+            args = (_ptr(y2.t), _ptr(sc2), _ptr(sh2), _ptr(src0.t), _ptr(out.t), _ptr(out.stats), 1e-5, B, H * W, cout)
+            self.ops.append(lambda s: check(L.idiff_block_tail(*args, s), "block_tail"))
+            self.n_launch += 1
+        else:
+            self.gemm(src0, src1, pk[prefix + ".res_conv"], out, k=1, res0=y2.t, res0_scale=sc2, res0_shift=sh2,
+                      out_stats=out.stats, NT=cout)
+        self.named[prefix] = out
+        return out
+
+    def linear_attn(self, prefix, x: _Act) -> _Act:
+        pk, B, H, W, Cc, L = self.net.pk, self.B, x.H, x.W, x.C, self.L
+        f = prefix + ".fn"
+        qkv = self.act(H, W, 384, tmp_name="la_qkv")
+        self.gemm(x, None, pk[f + ".to_qkv"], qkv, k=1, bias=False, row_stats=x.stats, epi=EPI_QSOFTMAX,
+                  qscale=32 ** -0.5)
+        weff = self.tmp("la_weff", (B, Cc * 128))
+        nfl = L.idiff_linattn_scratch_floats(B, H * W)
+        scratch = self.tmp("la_scratch", (nfl,), torch.float32)
+        to = pk[f + ".to_out"]
+        args = (_ptr(qkv.t), _ptr(to["w_f32"]), _ptr(weff), _ptr(scratch), B, H * W, Cc)
+        self.ops.append(lambda s: check(L.idiff_linattn_context(*args, s), "linattn_context"))
+        self.n_launch += 2
+        out = self.act(H, W, Cc)
+        entry = dict(N=Cc, NT=Cc, w=weff, bias=to["bias"])
+        self.gemm(qkv, None, entry, out, k=1, cin0=128, src0_ld=384, w_image_stride=Cc * 128, epi=EPI_LN_OUT,
+                  ln_g=to["g"], res0=x.t, ln_eps=1e-5)
+        self.named[prefix] = out
+        return out
+
+    def spatial_attn(self, prefix, x: _Act) -> _Act:
+        pk, B, H, W, Cc, L = self.net.pk, self.B, x.H, x.W, x.C, self.L
+        f = prefix + ".fn"
+        rows, HW = B * H * W, H * W
+        y = self.act(H, W, Cc, tmp_name="st_y")
+        a_ln = (_ptr(x.t), _ptr(pk[prefix + ".prenorm"]["g"]), _ptr(y.t), 1e-5, rows, Cc)
+        self.ops.append(lambda s: check(L.idiff_chan_ln(*a_ln, s), "chan_ln"))
+        ntile = L.idiff_gn_stats_ntile(HW)
+        part = self.tmp("st_gnp", (B, ntile, 32, 2), torch.float32)
+        a_gs = (_ptr(y.t), _ptr(part), B, HW, Cc, 32)
+        self.ops.append(lambda s: check(L.idiff_gn_stats(*a_gs, s), "gn_stats"))
+        self.n_launch += 2
+        sc, sh = self.gn_finalize(part, ntile, pk[f + ".norm"], Cc, 32, HW * (Cc // 32), 1e-6, tag="gn32")
+        h0 = self.act(H, W, Cc, stats=True, tmp_name=None)
+        self.gemm(y, None, pk[f + ".proj_in"], h0, k=1, a_scale=sc, a_shift=sh, a_silu=0, out_stats=h0.stats)
+        qkv = self.act(H, W, 3 * Cc, tmp_name="st_qkv")
+        self.gemm(h0, None, pk[f + ".attn1.qkv"], qkv, k=1, row_stats=h0.stats)
+        att = self.act(H, W, Cc, tmp_name="st_att")
+        a_at = (_ptr(qkv.t), _ptr(att.t), B, HW, Cc // 32, 32 ** -0.5)
+        self.ops.append(lambda s: check(L.idiff_self_attention(*a_at, s), "self_attention"))
+        self.n_launch += 1
+        h2 = self.act(H, W, Cc, stats=True)
+        self.gemm(att, None, pk[f + ".attn1.to_out"], h2, k=1, res0=h0.t, out_stats=h2.stats, bias_img_slot=prefix)
+        ff = self.act(H, W, 4 * Cc, tmp_name="st_ff")
+        self.gemm(h2, None, pk[f + ".ff.proj"], ff, k=1, row_stats=h2.stats, epi=EPI_GEGLU, out_ld=4 * Cc)
+        h3 = self.act(H, W, Cc, tmp_name="st_h3")
+        self.gemm(ff, None, pk[f + ".ff.out"], h3, k=1, res0=h2.t)
+        out = self.act(H, W, Cc)
+        self.gemm(h3, None, pk[f + ".proj_out"], out, k=1, res0=y.t, res1=x.t)
+        self.named[prefix] = out
+        return out
+
+    def conv(self, name, x: _Act, cout, k=3, stride=1, up=0) -> _Act:
+        H = x.H // 2 if stride == 2 else (x.H * 2 if up else x.H)
+        W = x.W // 2 if stride == 2 else (x.W * 2 if up else x.W)
+        out = self.act(H, W, cout)
+        self.gemm(x, None, self.net.pk[name], out, k=k, stride=stride, up=up)
+        self.named[name[:-5] if name.endswith(".conv") else name] = out
+        return out
+
+    # ---- whole network
+    def _build(self):
+        net, B, H, W, L = self.net, self.B, self.H, self.W, self.L
+        pk, nf = net.pk, net.nf
+        self.x_in = None
+        self.eps = self.new((B, 1, H, W), torch.float32)
+        Bt = 1 if self.shared_time else B
+        self.temb = self.new((Bt, net.td), torch.float32)
+        self.ss = self.new((Bt, net.S), torch.float32)
+        tm = pk["time"]
+        self._time_args = (_ptr(tm["w1t"]), _ptr(tm["b1"]), _ptr(tm["w2t"]), _ptr(tm["b2"]), _ptr(tm["wss"]),
+                           _ptr(tm["bss"]), _ptr(self.temb), _ptr(self.ss), Bt, nf, net.S)
+        self.n_launch += 2
+
+        x_first = self.act(H, W, nf)
+        self.named["init_conv"] = x_first
+        self._stem_tail = (_ptr(pk["init_conv"]["w"]), _ptr(pk["init_conv"]["bias"]), _ptr(x_first.t), B, H, W, nf)
+        self.n_launch += 1
+
+        h = x_first
+        skips = []
+        n = len(net.io)
+        for i, (di, do) in enumerate(net.io):
+            last = i == n - 1
+            h = self.resblock(f"downs.{i}.0", h, None, di)
+            skips.append(h)
+            h = self.resblock(f"downs.{i}.1", h, None, di, want_stats=not last)
+            h = self.spatial_attn(f"downs.{i}.2", h) if last else self.linear_attn(f"downs.{i}.2", h)
+            skips.append(h)
+            h = self.conv(f"downs.{i}.3", h, do, k=3) if last else self.conv(f"downs.{i}.3", h, do, k=4, stride=2)
+        h = self.resblock("mid_block1", h, None, net.dims[-1])
+        h = self.spatial_attn("mid_attn", h)
+        h = self.resblock("mid_block2", h, None, net.dims[-1])
+        for i, (di, do) in enumerate(reversed(net.io)):
+            lvl = n - 1 - i
+            last = lvl == n - 1
+            h = self.resblock(f"ups.{i}.0", h, skips.pop(), do)
+            h = self.resblock(f"ups.{i}.1", h, skips.pop(), do, want_stats=not last)
+            h = self.spatial_attn(f"ups.{i}.2", h) if last else self.linear_attn(f"ups.{i}.2", h)
+            h = self.conv(f"ups.{i}.3.conv", h, di, k=3, up=1) if lvl > 0 else self.conv(f"ups.{i}.3", h, di, k=3)
+        xa = self.act(H, W, nf)
+        a_add = (_ptr(h.t), _ptr(x_first.t), _ptr(xa.t), None, 1e-5, B * H * W, nf)
+        self.ops.append(lambda s: check(L.idiff_add_rows(*a_add, s), "add_rows"))
+        h = self.resblock("final_res", xa, x_first, nf)
+        a_head = (_ptr(h.t), _ptr(pk["final_conv"]["w"]), pk["final_conv"]["bias"], _ptr(self.eps), B, H, W, nf)
+        self.ops.append(lambda s: check(L.idiff_head_conv3(*a_head, s), "head_conv3"))
+        self.n_launch += 2
+
+    def run(self, xt, cond, t_dev, t_scalar):
+        L = self.L
+        s = torch.cuda.current_stream(self.dev).cuda_stream
+        t_ptr = t_dev if (t_dev is None or isinstance(t_dev, int)) else t_dev.data_ptr()
+        check(L.idiff_time_embed(t_ptr, t_scalar, *self._time_args, s), "time_embed")
+        check(L.idiff_stem_conv7(xt.data_ptr(), cond.data_ptr(), *self._stem_tail, s), "stem_conv7")
+        for op in self.ops:
+            op(s)

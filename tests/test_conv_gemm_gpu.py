@@ -1,0 +1,225 @@
+"""tcgen05 implicit-GEMM engine (idiff_conv_gemm) vs an fp32 torch reference of the same op.
+
+Tolerance: inputs/weights are bf16 on both sides, accumulation fp32, output stored as bf16, so the
+bound is the bf16 rounding of the output: max |err| <= 1e-2 * max|ref| (north-star tolerance).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import bf16r, conv_reference, describe, no_tf32, rand_act, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+@pytest.fixture(autouse=True)
+def _setup():
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    no_tf32()
+    yield
+    from instancediff_b200 import _lib
+    _lib.watchdog()
+
+
+def _run(B, H, W, cin0, cin1, N, k, stride=1, up=0, affine=False, silu=False, NT=None, seed=0, swap=0, **extra):
+    from instancediff_b200 import ops
+    from instancediff_b200.packing import pack_conv_weight
+    g = torch.Generator().manual_seed(seed)
+    Hs, Ws = (H * stride, W * stride) if not up else (H // 2, W // 2)
+    src0 = rand_act(B, Hs, Ws, cin0, g)
+    src1 = rand_act(B, Hs, Ws, cin1, g) if cin1 else None
+    cin = cin0 + cin1
+    w = (torch.rand(N, cin, k, k, generator=g) * 2 - 1).cuda() / math.sqrt(cin * k * k)
+    bias = (torch.rand(N, generator=g) * 2 - 1).cuda() * 0.1
+    sc = sh = None
+    if affine:
+        sc = (torch.rand(B, cin, generator=g) + 0.5).cuda()
+        sh = (torch.rand(B, cin, generator=g) - 0.5).cuda()
+    NT = min(N, 256) if NT is None else NT
+    out = torch.zeros(B, H, W, N, dtype=torch.bfloat16, device="cuda")
+    p = ops.make_gemm_params(B=B, H=H, W=W, ksize=k, stride=stride, cin0=cin0, cin1=cin1, up0=up, N=N, NT=NT,
+                             a_silu=int(silu), epi=0, out_ld=N, src0=src0, src1=src1, a_scale=sc, a_shift=sh,
+                             w=pack_conv_weight(w, NT).cuda(), bias=bias, out=out, dbg_swap_lbo_sbo=swap, **extra)
+    ops.conv_gemm(p)
+    torch.cuda.synchronize()
+    ref = conv_reference(src0, src1, w, bias, k, stride, up, sc, sh, silu)
+    return out, ref, dict(src0=src0, src1=src1, w=w, bias=bias, sc=sc, sh=sh, p=p)
+
+
+def test_probe_descriptor_convention():
+    """Bring-up probe: the simplest GEMM (1x1, 64->64, one tile).  If the documented LBO/SBO roles were
+    wrong the swapped variant would match instead -- the message says which."""
+    out, ref, _ = _run(1, 16, 8, 64, 0, 64, 1)
+    e0 = rel_err(out, ref)
+    if e0 > TOL:
+        out2, ref2, _ = _run(1, 16, 8, 64, 0, 64, 1, swap=1)
+        e1 = rel_err(out2, ref2)
+        pytest.fail(f"primary descriptor convention rel_err={e0:.4g}; swapped LBO/SBO rel_err={e1:.4g}\n"
+                    + describe(out, ref, "primary") + "\n" + describe(out2, ref2, "swapped"))
+
+
+CASES = [
+    # B, H, W, cin0, cin1, N, k, stride, up, affine, silu
+    (1, 16, 8, 64, 0, 64, 1, 1, 0, False, False),
+    (2, 32, 32, 64, 0, 64, 3, 1, 0, False, False),
+    (2, 32, 32, 64, 0, 64, 3, 1, 0, True, True),
+    (1, 32, 16, 128, 0, 128, 3, 1, 0, True, True),
+    (1, 16, 16, 256, 0, 256, 3, 1, 0, False, False),
+    (2, 32, 32, 64, 64, 64, 3, 1, 0, False, False),       # skip-concat
+    (1, 16, 16, 256, 128, 256, 3, 1, 0, False, False),    # 384 -> 256
+    (1, 16, 16, 256, 256, 256, 3, 1, 0, False, False),    # 512 -> 256, K = 4608
+    (1, 32, 32, 128, 64, 128, 1, 1, 0, False, False),     # 1x1 shortcut on a concat
+    (2, 16, 16, 64, 0, 64, 4, 2, 0, False, False),        # 4x4 stride-2 downsample
+    (1, 16, 16, 64, 0, 128, 4, 2, 0, False, False),
+    (1, 8, 8, 128, 0, 256, 4, 2, 0, False, False),
+    (1, 32, 32, 256, 0, 128, 3, 1, 1, False, False),      # nearest x2 upsample + 3x3
+    (1, 24, 20, 64, 0, 64, 3, 1, 0, True, True),          # ragged tiles (H % 16, W % 8 != 0)
+    (1, 4, 4, 256, 0, 256, 3, 1, 0, False, False),        # image smaller than one tile
+    (1, 32, 32, 64, 0, 384, 1, 1, 0, False, False),       # N split over 3 tiles of 128
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_matches_fp32_reference(case):
+    B, H, W, c0, c1, N, k, s, up, aff, silu = case
+    NT = 128 if N == 384 else None
+    out, ref, _ = _run(B, H, W, c0, c1, N, k, s, up, aff, silu, NT=NT)
+    assert rel_err(out, ref) <= TOL, describe(out, ref, str(case))
+
+
+def test_cuda_core_reference_agrees():
+    """idiff_conv_ref (plain CUDA-core loop nest) is an independent check of the same params struct."""
+    from instancediff_b200 import ops
+    out, ref, d = _run(1, 16, 16, 64, 64, 64, 3, affine=True, silu=True)
+    o32 = torch.empty(1, 16, 16, 64, dtype=torch.float32, device="cuda")
+    w_nhwc = bf16r(d["w"]).permute(0, 2, 3, 1).contiguous()
+    ops.conv_ref(d["p"], w_nhwc, o32)
+    torch.cuda.synchronize()
+    assert rel_err(o32, ref) <= 2e-3, describe(o32, ref, "conv_ref")
+    assert rel_err(out, o32) <= TOL, describe(out, o32, "tc vs conv_ref")
+
+
+def test_groupnorm_partials():
+    from instancediff_b200 import ops
+    B, H, W, N = 2, 32, 24, 128
+    tiles = ((H + 15) // 16) * ((W + 7) // 8)
+    part = torch.zeros(B, tiles, 8, 2, device="cuda")
+    out, ref, _ = _run(B, H, W, 64, 0, N, 3, gn_groups=8, gn_partial=part)
+    s = part.sum(dim=1)                                       # [B, 8, 2]
+    r = ref.reshape(B, H * W, 8, N // 8)
+    assert torch.allclose(s[..., 0], r.sum(dim=(1, 3)), rtol=1e-3, atol=1e-2), (s[..., 0], r.sum(dim=(1, 3)))
+    assert torch.allclose(s[..., 1], (r * r).sum(dim=(1, 3)), rtol=1e-3, atol=1e-2)
+    # finalize -> per-channel affine equals torch GroupNorm
+    gamma, beta = torch.rand(N, device="cuda") + 0.5, torch.rand(N, device="cuda") - 0.5
+    sc, sh = ops.gn_finalize(part, gamma, beta, H * W * (N // 8), 1e-5)
+    y = ref * sc[:, None, None, :] + sh[:, None, None, :]
+    gn = F.group_norm(ref.permute(0, 3, 1, 2), 8, gamma, beta, 1e-5).permute(0, 2, 3, 1)
+    assert rel_err(y, gn) <= 1e-3, describe(y, gn, "gn")
+
+
+def test_layernorm_fold_and_row_stats():
+    """acc' = (acc - mean*wsum)*rstd (+bias) equals Linear(LayerNorm(x)); out_row_stats are the LN stats."""
+    from instancediff_b200 import ops
+    from instancediff_b200.packing import fold_layernorm, pack_conv_weight
+    g = torch.Generator().manual_seed(3)
+    B, H, W, Cc, N = 2, 16, 16, 256, 256
+    x = rand_act(B, H, W, Cc, g)
+    gain, beta = torch.rand(Cc, generator=g).cuda() + 0.5, torch.rand(Cc, generator=g).cuda() - 0.5
+    w = ((torch.rand(N, Cc, generator=g) * 2 - 1) / 16).cuda()
+    xf = x.float().reshape(-1, Cc)
+    mean, var = xf.mean(1), xf.var(1, unbiased=False)
+    stats = torch.stack([mean, torch.rsqrt(var + 1e-5)], 1).contiguous()
+    wf, wsum, extra = fold_layernorm(w, gain, beta)
+    out = torch.zeros(B, H, W, N, dtype=torch.bfloat16, device="cuda")
+    ostats = torch.zeros(B * H * W, 2, device="cuda")
+    p = ops.make_gemm_params(B=B, H=H, W=W, ksize=1, stride=1, cin0=Cc, N=N, NT=256, out_ld=N, src0=x,
+                             w=pack_conv_weight(wf, 256).cuda(), bias=extra.contiguous(), row_stats=stats, wsum=wsum.contiguous(),
+                             out=out, out_row_stats=ostats, ln_eps=1e-5)
+    ops.conv_gemm(p)
+    torch.cuda.synchronize()
+    ref = F.linear(F.layer_norm(xf, (Cc,), gain, beta, 1e-5), w).reshape(B, H, W, N)
+    assert rel_err(out, ref) <= 1.5e-2, describe(out, ref, "ln-fold")
+    rf = ref.reshape(-1, N)
+    assert torch.allclose(ostats[:, 0], rf.mean(1), atol=2e-2)
+    assert torch.allclose(ostats[:, 1], torch.rsqrt(rf.var(1, unbiased=False) + 1e-5), rtol=3e-2)
+
+
+def test_epilogues_qsoftmax_geglu_lnout_residuals():
+    from instancediff_b200 import ops
+    from instancediff_b200.packing import interleave_geglu, pack_conv_weight
+    g = torch.Generator().manual_seed(5)
+    B, H, W, Cc = 1, 16, 16, 64
+    x = rand_act(B, H, W, Cc, g)
+    # q-softmax on columns [0,128)
+    w = ((torch.rand(384, Cc, generator=g) * 2 - 1)).cuda()
+    out = torch.zeros(B, H, W, 384, dtype=torch.bfloat16, device="cuda")
+    p = ops.make_gemm_params(B=B, H=H, W=W, ksize=1, stride=1, cin0=Cc, N=384, NT=128, epi=1, out_ld=384, src0=x,
+                             w=pack_conv_weight(w, 128).cuda(), out=out, qscale=32 ** -0.5)
+    ops.conv_gemm(p)
+    raw = F.linear(x.float(), bf16r(w))
+    ref = raw.clone()
+    ref[..., :128] = raw[..., :128].reshape(B, H, W, 4, 32).softmax(-1).reshape(B, H, W, 128) * 32 ** -0.5
+    torch.cuda.synchronize()
+    assert rel_err(out[..., :128], ref[..., :128]) <= TOL, describe(out[..., :128], ref[..., :128], "qsoftmax")
+    assert rel_err(out[..., 128:], ref[..., 128:]) <= TOL, describe(out[..., 128:], ref[..., 128:], "kv")
+
+    # GEGLU
+    wf = ((torch.rand(512, Cc, generator=g) * 2 - 1) / 8).cuda()
+    bf = (torch.rand(512, generator=g) - 0.5).cuda()
+    wi, bi = interleave_geglu(wf, bf)
+    out = torch.zeros(B, H, W, 256, dtype=torch.bfloat16, device="cuda")
+    p = ops.make_gemm_params(B=B, H=H, W=W, ksize=1, stride=1, cin0=Cc, N=512, NT=256, epi=2, out_ld=256, src0=x,
+                             w=pack_conv_weight(wi, 256).cuda(), bias=bi.contiguous(), out=out)
+    ops.conv_gemm(p)
+    a, gate = (F.linear(x.float(), bf16r(wf)) + bf).chunk(2, dim=-1)
+    ref = a * F.gelu(gate)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) <= TOL, describe(out, ref, "geglu")
+
+    # LN_OUT + residual, per-image weights, strided source (q columns of a [.,384] tensor)
+    B = 2
+    qkv = rand_act(B, H, W, 384, g)
+    xres = rand_act(B, H, W, Cc, g)
+    wimg = ((torch.rand(B, Cc, 128, generator=g) * 2 - 1) / 8).cuda()
+    wp = torch.stack([pack_conv_weight(wimg[b], Cc) for b in range(B)]).cuda()
+    bias = (torch.rand(Cc, generator=g) - 0.5).cuda()
+    gain = (torch.rand(Cc, generator=g) + 0.5).cuda()
+    out = torch.zeros(B, H, W, Cc, dtype=torch.bfloat16, device="cuda")
+    p = ops.make_gemm_params(B=B, H=H, W=W, ksize=1, stride=1, cin0=128, src0_ld=384, N=Cc, NT=Cc, epi=3, out_ld=Cc,
+                             src0=qkv, w=wp, w_image_stride=Cc * 128, bias=bias, ln_g=gain, res0=xres, out=out,
+                             ln_eps=1e-5)
+    ops.conv_gemm(p)
+    y = torch.einsum("bhwk,bck->bhwc", qkv[..., :128].float(), bf16r(wimg)) + bias
+    ref = (y - y.mean(-1, keepdim=True)) / (y.var(-1, unbiased=False, keepdim=True) + 1e-5).sqrt() * gain + xres.float()
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) <= TOL, describe(out, ref, "ln_out")
+
+
+def test_resblock_tail_in_shortcut_epilogue_and_image_bias():
+    """1x1 shortcut conv whose epilogue adds silu(GN(y2)) (res0 affine) and a per-image bias."""
+    from instancediff_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    B, H, W, N = 2, 16, 16, 128
+    y2 = rand_act(B, H, W, N, g)
+    sc2 = (torch.rand(B, N, generator=g) + 0.5).cuda()
+    sh2 = (torch.rand(B, N, generator=g) - 0.5).cuda()
+    bimg = (torch.rand(B, N, generator=g) - 0.5).cuda()
+    r1 = rand_act(B, H, W, N, g)
+    out, ref, _ = _run(B, H, W, 128, 64, N, 1, seed=11, res0=y2, res0_scale=sc2, res0_shift=sh2, res1=r1, bias_img=bimg)
+    ref = ref + F.silu(y2.float() * sc2[:, None, None, :] + sh2[:, None, None, :]) + r1.float() + bimg[:, None, None, :]
+    assert rel_err(out, ref) <= TOL, describe(out, ref, "shortcut+tail")
+
+
+def test_bad_arguments_return_errors():
+    from instancediff_b200 import _lib, ops
+    x = torch.zeros(1, 16, 8, 64, dtype=torch.bfloat16, device="cuda")
+    p = ops.make_gemm_params(B=1, H=16, W=8, ksize=5, stride=1, cin0=64, N=64, NT=64, out_ld=64, src0=x, w=x, out=x)
+    with pytest.raises(_lib.IdiffError):
+        ops.conv_gemm(p)
+    p = ops.make_gemm_params(B=1, H=16, W=8, ksize=1, stride=1, cin0=48, N=64, NT=64, out_ld=64, src0=x, w=x, out=x)
+    with pytest.raises(_lib.IdiffError):
+        ops.conv_gemm(p)

@@ -1,0 +1,149 @@
+"""Elementwise / normalisation / attention kernels vs fp32 torch references of the same op."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import bf16r, describe, no_tf32, rand_act, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _setup():
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    no_tf32()
+    yield
+    from instancediff_b200 import _lib
+    _lib.watchdog()
+
+
+def test_stem_conv7():
+    from instancediff_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    B, H, W = 2, 40, 24
+    x, mu = torch.randn(B, 1, H, W, generator=g).cuda(), torch.randn(B, 1, H, W, generator=g).cuda()
+    w = ((torch.rand(64, 2, 7, 7, generator=g) * 2 - 1) / 10).cuda()
+    b = (torch.rand(64, generator=g) - 0.5).cuda()
+    out = ops.stem_conv7(x, mu, w.permute(0, 2, 3, 1).contiguous(), b)
+    ref = F.conv2d(torch.cat([x - mu, mu], 1), w, b, padding=3).permute(0, 2, 3, 1)
+    assert rel_err(out, ref) <= 5e-3, describe(out, ref, "stem")
+
+
+def test_head_conv3():
+    from instancediff_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    B, H, W = 2, 24, 40
+    src = rand_act(B, H, W, 64, g)
+    w = ((torch.rand(1, 64, 3, 3, generator=g) * 2 - 1) / 24).cuda()
+    out = ops.head_conv3(src, w[0].permute(1, 2, 0).contiguous(), 0.25)
+    ref = F.conv2d(src.float().permute(0, 3, 1, 2), w, torch.tensor([0.25], device="cuda"), padding=1)
+    assert rel_err(out, ref) <= 1e-4, describe(out, ref, "head")
+
+
+@pytest.mark.parametrize("shared", [True, False])
+def test_time_embedding(shared):
+    from instancediff_b200 import ops
+    from oracle.unet_oracle import SinusoidalPosEmb
+    g = torch.Generator().manual_seed(2)
+    nf, S, B = 64, 96, 3
+    w1, b1 = (torch.randn(256, 64, generator=g) / 8).cuda(), torch.randn(256, generator=g).cuda() * 0.1
+    w2, b2 = (torch.randn(256, 256, generator=g) / 16).cuda(), torch.randn(256, generator=g).cuda() * 0.1
+    wss, bss = (torch.randn(S, 256, generator=g) / 16).cuda(), torch.randn(S, generator=g).cuda() * 0.1
+    if shared:
+        t, Bt, tv = None, 1, torch.tensor([37.0], device="cuda")
+        _, out = ops.time_embed(None, 37.0, w1.t().contiguous(), b1, w2.t().contiguous(), b2, wss, bss, 1, nf)
+    else:
+        tv = torch.tensor([1.0, 50.0, 100.0], device="cuda")
+        _, out = ops.time_embed(tv, 0.0, w1.t().contiguous(), b1, w2.t().contiguous(), b2, wss, bss, B, nf)
+    temb = F.linear(F.gelu(F.linear(SinusoidalPosEmb(64)(tv), w1, b1)), w2, b2)
+    ref = F.linear(F.silu(temb), wss, bss)
+    assert rel_err(out, ref) <= 1e-4, describe(out, ref, "time_embed")
+
+
+@pytest.mark.parametrize("C,G", [(64, 8), (128, 8), (256, 8), (256, 32)])
+def test_gn_stats_and_finalize(C, G):
+    from instancediff_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 2, 20, 12
+    x = rand_act(B, H, W, C, g)
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).cuda(), (torch.rand(C, generator=g) - 0.5).cuda()
+    ts, tb = (torch.rand(B, 2 * C, generator=g) - 0.5).cuda(), None
+    part = ops.gn_stats(x, G)
+    sc, sh = ops.gn_finalize(part, gamma, beta, H * W * (C // G), 1e-6)
+    y = x.float() * sc[:, None, None, :] + sh[:, None, None, :]
+    ref = F.group_norm(x.float().permute(0, 3, 1, 2), G, gamma, beta, 1e-6).permute(0, 2, 3, 1)
+    assert rel_err(y, ref) <= 1e-4, describe(y, ref, "gn")
+    # with time modulation: GN(x)*(1+scale)+shift ; row layout [B][2C] = (scale | shift), t_ld = 2C
+    ss = ts.contiguous()
+    sc2, sh2 = ops.gn_finalize(part, gamma, beta, H * W * (C // G), 1e-6, t_scale=ss, t_shift=ss[:, C:], t_ld=2 * C)
+    y2 = x.float() * sc2[:, None, None, :] + sh2[:, None, None, :]
+    ref2 = ref * (1 + ss[:, None, None, :C]) + ss[:, None, None, C:]
+    assert rel_err(y2, ref2) <= 1e-4, describe(y2, ref2, "gn+time")
+
+
+@pytest.mark.parametrize("C", [64, 128, 256])
+def test_block_tail_add_rows_chan_ln(C):
+    from instancediff_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    B, H, W = 2, 12, 20
+    y, res = rand_act(B, H, W, C, g), rand_act(B, H, W, C, g)
+    sc, sh = (torch.rand(B, C, generator=g) + 0.5).cuda(), (torch.rand(B, C, generator=g) - 0.5).cuda()
+    out, st = ops.block_tail(y, sc, sh, res, want_stats=True)
+    ref = F.silu(y.float() * sc[:, None, None, :] + sh[:, None, None, :]) + res.float()
+    assert rel_err(out, ref) <= 8e-3, describe(out, ref, "block_tail")
+    rf = ref.reshape(-1, C)
+    assert torch.allclose(st[:, 0], rf.mean(1), atol=5e-3)
+    assert torch.allclose(st[:, 1], torch.rsqrt(rf.var(1, unbiased=False) + 1e-5), rtol=2e-2)
+    o2, _ = ops.add_rows(y, res)
+    assert rel_err(o2, y.float() + res.float()) <= 8e-3
+    gain = (torch.rand(C, generator=g) + 0.5).cuda()
+    o3 = ops.chan_ln(y, gain)
+    yf = y.float()
+    ref3 = (yf - yf.mean(-1, keepdim=True)) / (yf.var(-1, unbiased=False, keepdim=True) + 1e-5).sqrt() * gain
+    assert rel_err(o3, ref3) <= 8e-3, describe(o3, ref3, "chan_ln")
+
+
+@pytest.mark.parametrize("C,HW", [(64, (24, 24)), (128, (16, 8)), (256, (72, 64))])
+def test_linear_attention_context(C, HW):
+    """Weff[b] = Wout * blockdiag(ctx^T) with ctx = softmax_n(k) v^T / HW  (oracle LinearAttention)."""
+    from instancediff_b200 import ops
+    from instancediff_b200.packing import unpack_conv_weight
+    g = torch.Generator().manual_seed(5)
+    B, (H, W) = 2, HW
+    qkv = rand_act(B, H, W, 384, g, scale=2.0)
+    w_out = ((torch.rand(C, 128, generator=g) * 2 - 1) / 8).cuda()
+    weff = ops.linattn_context(qkv, w_out)
+    torch.cuda.synchronize()
+    k = qkv[..., 128:256].float().reshape(B, H * W, 4, 32).permute(0, 2, 3, 1)      # b h d n
+    v = qkv[..., 256:].float().reshape(B, H * W, 4, 32).permute(0, 2, 3, 1) / (H * W)
+    ctx = torch.einsum("bhdn,bhen->bhde", k.softmax(-1), v)
+    ref = torch.einsum("che,bhde->bchd", w_out.reshape(C, 4, 32), ctx).reshape(B, C, 128)
+    got = torch.stack([unpack_conv_weight(weff[b], C, 128, 1, C)[:, :, 0, 0] for b in range(B)])
+    assert rel_err(got, ref) <= 1e-2, describe(got, ref, "weff")
+
+
+@pytest.mark.parametrize("L", [16, 128, 200, 1024])
+def test_self_attention(L):
+    from instancediff_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    B, heads = 2, 8
+    C = heads * 32
+    qkv = (torch.randn(B, L, 3 * C, generator=g)).cuda().to(torch.bfloat16)
+    out = ops.self_attention(qkv, heads, 32 ** -0.5)
+    torch.cuda.synchronize()
+    q, k, v = (t.float().reshape(B, L, heads, 32).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1))
+    ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B, L, C)
+    err = rel_err(out, ref)
+    if err > 1.5e-2:
+        from instancediff_b200 import _lib
+        msgs = [describe(out, ref, "primary")]
+        for flags in (2, 4, 6):
+            _lib.lib().idiff_set_debug_flags(flags)
+            o2 = ops.self_attention(qkv, heads, 32 ** -0.5)
+            torch.cuda.synchronize()
+            msgs.append(f"debug flags {flags}: rel_err={rel_err(o2, ref):.4g}")
+        _lib.lib().idiff_set_debug_flags(0)
+        pytest.fail("\n".join(msgs))
