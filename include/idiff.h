@@ -191,6 +191,12 @@ size_t idiff_linattn_scratch_floats(int B, int HW);
  * [B][L][C].  tcgen05 QK^T and PV with fp32 softmax. */
 int idiff_self_attention(const void* qkv, void* out, int B, int L, int heads, float scale, void* stream);
 
+/* Cross-attention to the single image-embedding token: out[b] = Wo (Wv ctx[b]) + bo  (softmax over one
+ * key is 1, so this is CrossAttn(x, ctx) for every pixel and every step).
+ * ctx [B][D], wv [C][D], wo [C][C], bo [C], out [B][C]; fixed summation order (sharding-invariant). */
+int idiff_cross_vec(const float* ctx, const float* wv, const float* wo, const float* bo, float* out, int B, int D,
+                    int C, void* stream);
+
 /* fp32 <-> bf16 / layout helpers */
 int idiff_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
 int idiff_bf16_to_f32(const void* src, float* dst, size_t n, void* stream);

@@ -207,10 +207,39 @@ time_proj_kernel(const float* __restrict__ temb_act, const float* __restrict__ w
   }
 }
 
+// ---- cross-attention to ONE context token -------------------------------------------------------
+// softmax over a single key == 1, so CrossAttn(x, ctx)[b] = Wo (Wv ctx_b) + bo for every pixel and step.
+// grid = B, block = C threads; fixed summation order => result independent of the batch sharding.
+__global__ void cross_vec_kernel(const float* __restrict__ ctx, const float* __restrict__ wv,
+                                 const float* __restrict__ wo, const float* __restrict__ bo,
+                                 float* __restrict__ out, int D, int C) {
+  extern __shared__ float csm[];
+  float* cs = csm;          // [D]
+  float* vs = csm + D;      // [C]
+  const int b = blockIdx.x, j = threadIdx.x;
+  for (int k = j; k < D; k += blockDim.x) cs[k] = ctx[(size_t)b * D + k];
+  __syncthreads();
+  float a = 0.f;
+  for (int k = 0; k < D; ++k) a = fmaf(wv[(size_t)j * D + k], cs[k], a);
+  vs[j] = a;
+  __syncthreads();
+  float o = bo[j];
+  for (int i = 0; i < C; ++i) o = fmaf(wo[(size_t)j * C + i], vs[i], o);
+  out[(size_t)b * C + j] = o;
+}
+
 }  // namespace idiff
 
 extern "C" {
 using namespace idiff;
+
+int idiff_cross_vec(const float* ctx, const float* wv, const float* wo, const float* bo, float* out, int B, int D,
+                    int C, void* stream) {
+  IDIFF_REQUIRE(ctx && wv && wo && bo && out && B > 0 && D > 0, "cross_vec: bad arguments");
+  IDIFF_REQUIRE(C > 0 && C <= 1024 && C % 32 == 0, "cross_vec: unsupported C %d", C);
+  cross_vec_kernel<<<B, C, (D + C) * sizeof(float), as_stream(stream)>>>(ctx, wv, wo, bo, out, D, C);
+  return check_launch("cross_vec");
+}
 
 int idiff_f32_to_bf16(const float* src, void* dst, size_t n, void* stream) {
   IDIFF_REQUIRE(src && dst, "f32_to_bf16: null");

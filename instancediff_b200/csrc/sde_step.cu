@@ -164,8 +164,8 @@ int idiff_sde_step(float* x_out, const float* x, const float* eps, const float* 
                    const float* coef, int input_is_score, int use_philox, uint64_t seed, uint64_t elem_offset,
                    size_t n, void* stream) {
   using namespace idiff;
+  if (n == 0) return IDIFF_OK;                       // empty batch: nothing to do (pointers may be null)
   IDIFF_REQUIRE(x_out && x && eps && coef, "sde_step: null pointer");
-  if (n == 0) return IDIFF_OK;
   const bool vec = (n % 4 == 0) && aligned16(x_out) && aligned16(x) && aligned16(eps) && (!mu || aligned16(mu)) &&
                    (!z || aligned16(z)) && (elem_offset % 4 == 0);
   if (vec) {
@@ -210,8 +210,8 @@ int idiff_step_select(const float* table, int* t_counter, float* cur_row, float*
 int idiff_noise_state(float* x_out, const float* mu, const float* z, float max_sigma, int use_philox,
                       uint64_t seed, uint64_t elem_offset, size_t n, void* stream) {
   using namespace idiff;
-  IDIFF_REQUIRE(x_out && mu && (z || use_philox), "noise_state: null pointer");
   if (n == 0) return IDIFF_OK;
+  IDIFF_REQUIRE(x_out && mu && (z || use_philox), "noise_state: null pointer");
   noise_state_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x_out, mu, z, max_sigma, use_philox, seed,
                                                                       elem_offset, n);
   return check_launch("noise_state");
@@ -219,8 +219,8 @@ int idiff_noise_state(float* x_out, const float* mu, const float* z, float max_s
 
 int idiff_philox_normal(float* out, uint64_t seed, uint64_t elem_offset, uint32_t step, size_t n, void* stream) {
   using namespace idiff;
-  IDIFF_REQUIRE(out, "philox_normal: null pointer");
   if (n == 0) return IDIFF_OK;
+  IDIFF_REQUIRE(out, "philox_normal: null pointer");
   philox_normal_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(out, seed, elem_offset, step, n);
   return check_launch("philox_normal");
 }

@@ -298,17 +298,19 @@ class ConditionalUNet:
         key = (ctx.data_ptr(), ctx._version, tuple(ctx.shape))
         if key == self._ctx_key:
             return
-        c = ctx.detach().to(self.device, torch.float32)
-        B = c.shape[0]
+        c = ctx.detach().to(self.device, torch.float32).contiguous()
+        B, D = c.shape
+        s = torch.cuda.current_stream(self.device).cuda_stream
         for name in self.spatial_layers():
             f = name + ".fn.attn2"
-            v = c @ self.params[f + ".to_v.weight"].t()
-            vec = v @ self.params[f + ".to_out.weight"].t() + self.params[f + ".to_out.bias"]
+            wv, wo, bo = (self.params[f + ".to_v.weight"], self.params[f + ".to_out.weight"],
+                          self.params[f + ".to_out.bias"])
             buf = self._crossvec.get((name, B))
             if buf is None:                      # persistent per batch size: captured graphs keep the pointer
-                buf = torch.empty_like(vec)
+                buf = torch.empty(B, wo.shape[0], dtype=torch.float32, device=self.device)
                 self._crossvec[(name, B)] = buf
-            buf.copy_(vec)
+            check(self.L.idiff_cross_vec(c.data_ptr(), wv.data_ptr(), wo.data_ptr(), bo.data_ptr(), buf.data_ptr(),
+                                         B, D, wo.shape[0], s), "cross_vec")
         self._ctx_key = key
         for plan in self._plans.values():
             if plan.B == B:
@@ -374,6 +376,7 @@ class _Plan:
         self.L = net.L
         self.dev = net.device
         self.ops: List = []
+        self.op_info: List[tuple] = []        # (kernel kind, algorithmic FLOPs, label) parallel to self.ops
         self.keep: List = []
         self.scratch: Dict[tuple, torch.Tensor] = {}
         self.ctx_slots: Dict[str, GemmParams] = {}
@@ -433,6 +436,8 @@ class _Plan:
         self.keep.append(p)
         L, ref = self.L, C.byref(p)
         self.ops.append(lambda s: check(L.idiff_conv_gemm(ref, s), "conv_gemm"))
+        flops = 2.0 * self.B * out.H * out.W * p.N * (p.cin0 + p.cin1) * k * k
+        self.op_info.append(("conv_gemm", flops, f"k{k}s{stride}u{up} {p.cin0 + p.cin1}->{p.N} @{out.H}x{out.W}"))
         self.n_launch += 1
 
     def bind_context(self, crossvec):
@@ -458,6 +463,7 @@ class _Plan:
         args = (_ptr(partial), ntile, _ptr(norm["g"]), _ptr(norm["b"]), ts, tb, t_ld, _ptr(sc), _ptr(sh), B, C, G,
                 count, eps)
         self.ops.append(lambda s: check(L.idiff_gn_finalize(*args, s), "gn_finalize"))
+        self.op_info.append(("gn_finalize", 0.0, f"C{C}"))
         self.n_launch += 1
         return sc, sh
 
@@ -480,6 +486,7 @@ class _Plan:
             L = self.L
             args = (_ptr(y2.t), _ptr(sc2), _ptr(sh2), _ptr(src0.t), _ptr(out.t), _ptr(out.stats), 1e-5, B, H * W, cout)
             self.ops.append(lambda s: check(L.idiff_block_tail(*args, s), "block_tail"))
+            self.op_info.append(("block_tail", 0.0, f"C{cout} @{H}x{W}"))
             self.n_launch += 1
         else:
             self.gemm(src0, src1, pk[prefix + ".res_conv"], out, k=1, res0=y2.t, res0_scale=sc2, res0_shift=sh2,
@@ -499,6 +506,7 @@ class _Plan:
         to = pk[f + ".to_out"]
         args = (_ptr(qkv.t), _ptr(to["w_f32"]), _ptr(weff), _ptr(scratch), B, H * W, Cc)
         self.ops.append(lambda s: check(L.idiff_linattn_context(*args, s), "linattn_context"))
+        self.op_info.append(("linattn_context", 2.0 * 2 * B * H * W * 128 * 32, f"C{Cc} @{H}x{W}"))
         self.n_launch += 2
         out = self.act(H, W, Cc)
         entry = dict(N=Cc, NT=Cc, w=weff, bias=to["bias"])
@@ -514,10 +522,12 @@ class _Plan:
         y = self.act(H, W, Cc, tmp_name="st_y")
         a_ln = (_ptr(x.t), _ptr(pk[prefix + ".prenorm"]["g"]), _ptr(y.t), 1e-5, rows, Cc)
         self.ops.append(lambda s: check(L.idiff_chan_ln(*a_ln, s), "chan_ln"))
+        self.op_info.append(("chan_ln", 0.0, f"C{Cc} @{H}x{W}"))
         ntile = L.idiff_gn_stats_ntile(HW)
         part = self.tmp("st_gnp", (B, ntile, 32, 2), torch.float32)
         a_gs = (_ptr(y.t), _ptr(part), B, HW, Cc, 32)
         self.ops.append(lambda s: check(L.idiff_gn_stats(*a_gs, s), "gn_stats"))
+        self.op_info.append(("gn_stats", 0.0, f"C{Cc} @{H}x{W}"))
         self.n_launch += 2
         sc, sh = self.gn_finalize(part, ntile, pk[f + ".norm"], Cc, 32, HW * (Cc // 32), 1e-6, tag="gn32")
         h0 = self.act(H, W, Cc, stats=True, tmp_name=None)
@@ -527,6 +537,7 @@ class _Plan:
         att = self.act(H, W, Cc, tmp_name="st_att")
         a_at = (_ptr(qkv.t), _ptr(att.t), B, HW, Cc // 32, 32 ** -0.5)
         self.ops.append(lambda s: check(L.idiff_self_attention(*a_at, s), "self_attention"))
+        self.op_info.append(("self_attention", 2.0 * 2 * B * HW * HW * Cc, f"L{HW}"))
         self.n_launch += 1
         h2 = self.act(H, W, Cc, stats=True)
         self.gemm(att, None, pk[f + ".attn1.to_out"], h2, k=1, res0=h0.t, out_stats=h2.stats, bias_img_slot=prefix)
@@ -590,10 +601,37 @@ class _Plan:
         xa = self.act(H, W, nf)
         a_add = (_ptr(h.t), _ptr(x_first.t), _ptr(xa.t), None, 1e-5, B * H * W, nf)
         self.ops.append(lambda s: check(L.idiff_add_rows(*a_add, s), "add_rows"))
+        self.op_info.append(("add_rows", 0.0, f"C{nf} @{H}x{W}"))
         h = self.resblock("final_res", xa, x_first, nf)
         a_head = (_ptr(h.t), _ptr(pk["final_conv"]["w"]), pk["final_conv"]["bias"], _ptr(self.eps), B, H, W, nf)
         self.ops.append(lambda s: check(L.idiff_head_conv3(*a_head, s), "head_conv3"))
+        self.op_info.append(("head_conv3", 2.0 * B * H * W * nf * 9, f"@{H}x{W}"))
         self.n_launch += 2
+
+    def run_timed(self, xt, cond, t_scalar, reps=3):
+        """Instrumented replay (bench/profiling): CUDA events around every launch on the launching stream.
+        Returns [(kind, label, flops, mean_ms)] including the time-embedding and stem launches."""
+        L = self.L
+        stream = torch.cuda.current_stream(self.dev)
+        s = stream.cuda_stream
+        calls = [("time_embed", "", 0.0, lambda: check(L.idiff_time_embed(None, t_scalar, *self._time_args, s))),
+                 ("stem_conv7", f"@{self.H}x{self.W}", 2.0 * self.B * self.H * self.W * 98 * self.net.nf,
+                  lambda: check(L.idiff_stem_conv7(xt.data_ptr(), cond.data_ptr(), *self._stem_tail, s)))]
+        for op, (kind, flops, label) in zip(self.ops, self.op_info):
+            calls.append((kind, label, flops, (lambda op=op: op(s))))
+        acc = [0.0] * len(calls)
+        for _ in range(reps):
+            evs = []
+            for _, _, _, fn in calls:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                evs.append((e0, e1))
+            torch.cuda.synchronize(self.dev)
+            for i, (e0, e1) in enumerate(evs):
+                acc[i] += e0.elapsed_time(e1)
+        return [(k, lbl, fl, a / reps) for (k, lbl, fl, _), a in zip(calls, acc)]
 
     def run(self, xt, cond, t_dev, t_scalar):
         L = self.L
