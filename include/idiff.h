@@ -73,6 +73,9 @@ int idiff_step_select(const float* table, int* t_counter, float* cur_row, float*
 /* Bring-up switches used by tests/test_umma_probe.py only (bit 1: swap LBO/SBO of the MN-major V
  * descriptor in self-attention; bit 2: swap LBO/SBO of its K-major descriptors). 0 in production. */
 int idiff_set_debug_flags(int flags);
+/* Per-role cycle counters of CTA 0 of the last idiff_conv_gemm launched with params.reserved0 = 1
+ * (16 x uint64, layout documented in csrc/conv_gemm.cu); synchronises the device. Profiling aid. */
+int idiff_debug_read_prof(unsigned long long* out16_host);
 
 /* ------------------------------------------------------------------------------------------
  * UNet building blocks (the model callable of IRSDE.score_fn, utils/sde_utils.py:198; network

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libidiff_sm100.so")
+LIB_PATH = os.environ.get("IDIFF_LIB_PATH") or os.path.join(_HERE, "libidiff_sm100.so")   # override: A/B builds
 
 c_f32p = C.c_void_p      # device pointers travel as integers (tensor.data_ptr())
 c_ptr = C.c_void_p
@@ -49,6 +49,7 @@ SIGNATURES = {
     "idiff_philox_normal": (C.c_int, [c_ptr, C.c_uint64, C.c_uint64, C.c_uint32, C.c_size_t, c_ptr]),
     "idiff_step_select": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_float, c_ptr]),
     "idiff_set_debug_flags": (C.c_int, [C.c_int]),
+    "idiff_debug_read_prof": (C.c_int, [c_ptr]),
     "idiff_conv_gemm": (C.c_int, [C.POINTER(GemmParams), c_ptr]),
     "idiff_sizeof_gemm_params": (C.c_int, []),
     "idiff_conv_gemm_smem_bytes": (C.c_int, [C.POINTER(GemmParams)]),

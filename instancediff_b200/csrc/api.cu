@@ -2,7 +2,6 @@
 #include "host_common.h"
 
 namespace idiff {
-__device__ int g_watchdog = 0;
 thread_local char g_err[512] = "";
 
 int fail(int code, const char* fmt, ...) {
@@ -28,15 +27,11 @@ int idiff_sizeof_gemm_params(void) { return (int)sizeof(idiff_gemm_params); }
 const char* idiff_last_error(void) { return idiff::g_err; }
 
 int idiff_watchdog_status(int clear) {
-  int v = 0;
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return idiff::fail(IDIFF_ERR_CUDA, "watchdog sync: %s", cudaGetErrorString(e));
-  e = cudaMemcpyFromSymbol(&v, idiff::g_watchdog, sizeof(int));
-  if (e != cudaSuccess) return idiff::fail(IDIFF_ERR_CUDA, "watchdog read: %s", cudaGetErrorString(e));
-  if (clear && v != 0) {
-    int z = 0;
-    cudaMemcpyToSymbol(idiff::g_watchdog, &z, sizeof(int));
-  }
+  const int a = idiff::watchdog_conv(clear), b = idiff::watchdog_attn(clear);
+  if (a < 0 || b < 0) return idiff::fail(IDIFF_ERR_CUDA, "watchdog read failed");
+  const int v = a != 0 ? a : b;
   if (v != 0) idiff::fail(IDIFF_ERR_WATCHDOG, "device pipeline wait timed out at site %d", v);
   return v;
 }

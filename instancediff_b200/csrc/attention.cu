@@ -23,6 +23,7 @@ constexpr int AT_BAR = AT_P + 16 * AT_PLANE;
 constexpr int AT_SMEM = AT_BAR + 64;
 
 static int g_debug_flags = 0;
+int watchdog_attn(int clear) { return watchdog_read_tu(clear); }
 
 __global__ void __launch_bounds__(128)
 self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int L, int heads,

@@ -14,7 +14,7 @@ namespace idiff {
 // flag and every later wait falls through, so a pipeline bug produces garbage + an error code
 // instead of hanging the GPU.  The host reads it through idiff_watchdog_status().
 // ---------------------------------------------------------------------------------------------
-extern __device__ int g_watchdog;   // defined in api.cu
+static __device__ int g_watchdog;   // one per translation unit (no -rdc: setmaxnreg needs whole-program compilation)
 
 IDIFF_DEVINL uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -55,14 +55,12 @@ IDIFF_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 IDIFF_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity, int code) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = globaltimer_ns();
-  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0) {
-      if (*((volatile int*)&g_watchdog) != 0) return;
-      if (globaltimer_ns() - t0 > 2000000000ull) {
-        atomicCAS(&g_watchdog, 0, code);
-        return;
-      }
+    // checked on EVERY spin: one try_wait may itself block for a hardware-defined interval
+    if (*((volatile int*)&g_watchdog) != 0) return;
+    if (globaltimer_ns() - t0 > 1000000000ull) {
+      atomicCAS(&g_watchdog, 0, code);
+      return;
     }
   }
 }
@@ -138,6 +136,37 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N, int b_mn_major
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Exactly one lane of a converged warp gets `true`.  The MMA / bulk-copy issuing warps stay warp-uniform and
+// predicate only the issue on this, so descriptors live in uniform registers (no R2UR waterfall).
+IDIFF_DEVINL bool elect_one() {
+  uint32_t p;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(p));
+  return p != 0;
+}
+
+// D[tmem] (+)= A[smem] * B[smem] with the descriptors given as (lo, hi) halves: hi is loop-invariant, lo only
+// changes by an immediate from MMA to MMA.
+IDIFF_DEVINL void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                 uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// descriptor halves (see umma_desc): lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version 1 << 14
+IDIFF_DEVINL uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+IDIFF_DEVINL uint32_t umma_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14); }
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 IDIFF_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -151,6 +180,17 @@ IDIFF_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uin
 IDIFF_DEVINL void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// Host hook: read (and optionally clear) this translation unit's watchdog word.
+static inline int watchdog_read_tu(int clear) {
+  int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_watchdog, sizeof(int)) != cudaSuccess) return -1;
+  if (clear && v != 0) {
+    const int z = 0;
+    cudaMemcpyToSymbol(g_watchdog, &z, sizeof(int));
+  }
+  return v;
 }
 
 // ---- small math / packing ----------------------------------------------------------------------
