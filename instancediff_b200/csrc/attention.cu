@@ -52,11 +52,17 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
   // tile loader: 128 rows x 32 channels -> [4 planes][128 rows][8]; rows >= L are zero
   auto load_tile = [&](int smem_off, int row0, int col_off) {
     const int c8 = tid & 3;
-    for (int r = tid >> 2; r < 128; r += 32) {
-      uint4 q = make_uint4(0u, 0u, 0u, 0u);
-      if (row0 + r < L) q = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(row0 + r) * ld + col_off + c8 * 8));
-      *reinterpret_cast<uint4*>(sm + smem_off + c8 * AT_PLANE + r * 16) = q;
+    uint4 q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                       // branch-free: clamped row, zeroed afterwards
+      const int row = row0 + (tid >> 2) + 32 * i;
+      const int rc = row < L ? row : L - 1;
+      q[i] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)rc * ld + col_off + c8 * 8));
+      if (row >= L) q[i] = make_uint4(0u, 0u, 0u, 0u);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<uint4*>(sm + smem_off + c8 * AT_PLANE + ((tid >> 2) + 32 * i) * 16) = q[i];
   };
 
   load_tile(AT_Q, q0, 0);
@@ -64,6 +70,16 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
   const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);
   const uint32_t idesc_o = umma_idesc_bf16(128, 32, 1);          // B (= V) is MN-major
   const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  // MMA issue: warp 0 runs the issue code warp-uniformly, one elected lane issues (descriptors stay uniform)
+  const bool leader = (warp == 0) && elect_one();
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+  const uint32_t smem0 = smem_u32(sm);
+  const bool swk = (dbg & 4) != 0, swv = (dbg & 2) != 0;
+  const uint32_t k_lbo = swk ? 128 : AT_PLANE, k_sbo = swk ? AT_PLANE : 128;     // K-major operands (Q, K, P)
+  const uint32_t v_lbo = swv ? AT_PLANE : 128, v_sbo = swv ? 128 : AT_PLANE;     // MN-major V
+  const uint32_t q_lo = umma_desc_lo(smem0 + AT_Q, k_lbo), kk_lo = umma_desc_lo(smem0 + AT_K, k_lbo);
+  const uint32_t p_lo = umma_desc_lo(smem0 + AT_P, k_lbo), v_lo = umma_desc_lo(smem0 + AT_V, v_lbo);
+  const uint32_t k_hi = umma_desc_hi(k_sbo), v_hi = umma_desc_hi(v_sbo);
 
   float o[32];
 #pragma unroll
@@ -77,16 +93,16 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
     load_tile(AT_V, k0, 2 * C);
     fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
+      if (leader) {
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const uint32_t l = (dbg & 4) ? 128 : AT_PLANE, s = (dbg & 4) ? AT_PLANE : 128;
-        const uint64_t ad = umma_desc(smem_u32(sm + AT_Q) + kk * 2 * AT_PLANE, l, s);
-        const uint64_t bd = umma_desc(smem_u32(sm + AT_K) + kk * 2 * AT_PLANE, l, s);
-        umma_bf16(tmem, ad, bd, idesc_s, kk);
+        for (int kk = 0; kk < 2; ++kk)
+          umma_bf16_lohi(tmem_u, q_lo + ((kk * 2 * AT_PLANE) >> 4), k_hi, kk_lo + ((kk * 2 * AT_PLANE) >> 4), k_hi, idesc_s,
+                         kk);
+        umma_commit(bar_s);
       }
-      umma_commit(bar_s);
+      __syncwarp();
     }
     mbar_wait(bar_s, j & 1, 201);
     tc_fence_after();
@@ -121,19 +137,17 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
     tc_fence_before();
     fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
+      if (leader) {
         // A: P planes (2kk, 2kk+1); B: V rows (keys) 16kk.. as MN-major: LBO = 8-key group pitch (128 B),
         // SBO = pitch between 8-channel groups (plane)
-        const uint32_t l = (dbg & 4) ? 128 : AT_PLANE, s = (dbg & 4) ? AT_PLANE : 128;
-        const uint64_t ad = umma_desc(smem_u32(sm + AT_P) + kk * 2 * AT_PLANE, l, s);
-        const uint64_t bd = (dbg & 2) ? umma_desc(smem_u32(sm + AT_V) + kk * 256, AT_PLANE, 128)
-                                      : umma_desc(smem_u32(sm + AT_V) + kk * 256, 128, AT_PLANE);
-        umma_bf16(tmem, ad, bd, idesc_o, kk);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16_lohi(tmem_u, p_lo + ((kk * 2 * AT_PLANE) >> 4), k_hi, v_lo + ((kk * 256) >> 4), v_hi, idesc_o, kk);
+        umma_commit(bar_o);
       }
-      umma_commit(bar_o);
+      __syncwarp();
     }
     mbar_wait(bar_o, j & 1, 202);
     tc_fence_after();
@@ -281,45 +295,43 @@ linattn_partial_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict_
   }
 }
 
-// grid = B, block = 256: merge partials -> ctx (smem), then Weff[c][h*32+d] = sum_e Wout[c][h*32+e] ctx[h][d][e]
+// grid = (4 heads, B), block = 256: merge partials -> ctx_h (smem), then
+// Weff[c][h*32+d] = sum_e Wout[c][h*32+e] ctx[h][d][e]   (the columns of this head)
 __global__ void __launch_bounds__(256)
 linattn_merge_kernel(const float* __restrict__ part, int nchunk, const float* __restrict__ w_out,
                      __nv_bfloat16* __restrict__ weff, int HW, int C) {
-  __shared__ float ctx[4 * 32 * 32];
-  __shared__ float mfin[128], sfin[128];
-  const int tid = threadIdx.x, b = blockIdx.x;
-  if (tid < 128) {
-    const int h = tid >> 5, d = tid & 31;
-    const float* p0 = part + ((size_t)b * 4 + h) * nchunk * LA_PART;
+  __shared__ float ctx[32 * 33];
+  __shared__ float mfin[32], sfin[32];
+  const int tid = threadIdx.x, h = blockIdx.x, b = blockIdx.y;
+  const float* p0 = part + ((size_t)b * 4 + h) * nchunk * LA_PART;
+  if (tid < 32) {
     float m = -INFINITY;
-    for (int c = 0; c < nchunk; ++c) m = fmaxf(m, p0[(size_t)c * LA_PART + d]);
+    for (int c = 0; c < nchunk; ++c) m = fmaxf(m, p0[(size_t)c * LA_PART + tid]);
     float s = 0.f;
-    for (int c = 0; c < nchunk; ++c) s += p0[(size_t)c * LA_PART + 32 + d] * __expf(p0[(size_t)c * LA_PART + d] - m);
+    for (int c = 0; c < nchunk; ++c) s += p0[(size_t)c * LA_PART + 32 + tid] * __expf(p0[(size_t)c * LA_PART + tid] - m);
     mfin[tid] = m;
     sfin[tid] = s;
   }
   __syncthreads();
-  for (int i = tid; i < 4096; i += 256) {
-    const int h = i >> 10, d = (i >> 5) & 31;
-    const float* p0 = part + ((size_t)b * 4 + h) * nchunk * LA_PART;
-    const float m = mfin[h * 32 + d];
-    float a = 0.f;
-    for (int c = 0; c < nchunk; ++c)
-      a += p0[(size_t)c * LA_PART + 64 + (i & 1023)] * __expf(p0[(size_t)c * LA_PART + d] - m);
-    ctx[i] = a / (sfin[h * 32 + d] * (float)HW);           // softmax normaliser and v / (h*w)
+  for (int i = tid; i < 1024; i += 256) {
+    const int d = i >> 5, e = i & 31;
+    const float m = mfin[d];
+    float acc = 0.f;
+    for (int c = 0; c < nchunk; ++c) acc += p0[(size_t)c * LA_PART + 64 + i] * __expf(p0[(size_t)c * LA_PART + d] - m);
+    ctx[d * 33 + e] = acc / (sfin[d] * (float)HW);           // softmax normaliser and v / (h*w)
   }
   __syncthreads();
   __nv_bfloat16* wdst = weff + (size_t)b * C * 128;
-  for (int i = tid; i < C * 128; i += 256) {
-    const int c = i >> 7, kc = i & 127, h = kc >> 5, d = kc & 31;
+  for (int i = tid; i < C * 32; i += 256) {
+    const int c = i >> 5, d = i & 31, kc = h * 32 + d;
     const float* wr = w_out + (size_t)c * 128 + h * 32;
-    const float* cr = ctx + (h * 32 + d) * 32;
-    float a = 0.f;
+    const float* cr = ctx + d * 33;
+    float acc = 0.f;
 #pragma unroll 8
-    for (int e = 0; e < 32; ++e) a = fmaf(wr[e], cr[e], a);
+    for (int e = 0; e < 32; ++e) acc = fmaf(__ldg(wr + e), cr[e], acc);
     // packed B-operand layout of conv_gemm (NT = C, two 64-wide K stages)
     const int ks = kc >> 6, kin = kc & 63;
-    wdst[(size_t)ks * C * 64 + (kin >> 3) * (C * 8) + c * 8 + (kin & 7)] = __float2bfloat16_rn(a);
+    wdst[(size_t)ks * C * 64 + (kin >> 3) * (C * 8) + c * 8 + (kin & 7)] = __float2bfloat16_rn(acc);
   }
 }
 
@@ -368,7 +380,8 @@ int idiff_linattn_context(const void* qkv, const float* w_out, void* weff_packed
   dim3 grid((unsigned)nchunk, 4u, (unsigned)B);
   linattn_partial_kernel<<<grid, 256, smem, as_stream(stream)>>>((const __nv_bfloat16*)qkv, scratch, HW);
   if (int rc = check_launch("linattn_partial")) return rc;
-  linattn_merge_kernel<<<B, 256, 0, as_stream(stream)>>>(scratch, nchunk, w_out, (__nv_bfloat16*)weff_packed, HW, C);
+  linattn_merge_kernel<<<dim3(4, (unsigned)B), 256, 0, as_stream(stream)>>>(scratch, nchunk, w_out,
+                                                                            (__nv_bfloat16*)weff_packed, HW, C);
   return check_launch("linattn_merge");
 }
 

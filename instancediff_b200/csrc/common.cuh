@@ -40,23 +40,25 @@ IDIFF_DEVINL void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-IDIFF_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or ~`ns` elapse,
+// so waiting warps do not burn issue slots that the working warps need.
+IDIFF_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t ns = 200000u) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
       : "memory");
   return ok != 0;
 }
-// Bounded wait.  `code` identifies the call site in the watchdog word.
+// Bounded wait (~1 s).  `code` identifies the call site in the watchdog word.  The clock and the watchdog word
+// are only looked at when a (sleeping) try comes back empty, i.e. at most every ~0.2 ms.
 IDIFF_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity, int code) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = globaltimer_ns();
   while (!mbar_try_wait(bar, parity)) {
-    // checked on EVERY spin: one try_wait may itself block for a hardware-defined interval
     if (*((volatile int*)&g_watchdog) != 0) return;
     if (globaltimer_ns() - t0 > 1000000000ull) {
       atomicCAS(&g_watchdog, 0, code);

@@ -34,8 +34,10 @@ constexpr int kWarpMma = kWarpB + 1;               // 17
 constexpr int kThreads = 20 * 32;                  // 5 warpgroups (warps 18-19 idle): setmaxnreg works per warpgroup
 constexpr int kMaxSA = 4, kMaxSB = 8;
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kHeader = 8192;                      // barriers, GroupNorm scratch, row-statistics exchange
-constexpr int kOffRed = 256, kOffXch = 4096;
+constexpr int kHeader = 12288;                     // barriers, GroupNorm scratch, row-statistics exchange
+constexpr int kOffRed = 256, kOffXch = 1536, kOffImg = 5632;   // red 512 B; xch 4 KB; per-image params 2 x 3 x 256 floats = 6 KB
+constexpr int kHeaderEnd = kOffImg + 2 * 3 * 256 * 4;
+static_assert(kHeaderEnd <= kHeader, "header overflow");
 
 template <int KS>
 struct GeomT {
@@ -53,7 +55,7 @@ struct GeomT {
 };
 
 struct SmemPlan {
-  int SA, SB, resident, stageA, stageB, offA, offB, total;
+  int SA, SB, resident, stageA, stageB, offA, offB, offP, total;
 };
 
 __host__ inline int stage_a_bytes(int ks) {
@@ -68,7 +70,8 @@ __host__ inline SmemPlan plan_smem(const idiff_gemm_params& p) {
   const int nk = nchunks * p.ksize * p.ksize;
   s.stageA = stage_a_bytes(p.ksize);
   s.stageB = p.NT * 128;
-  const int budget = kSmemLimit - kHeader;
+  const int pbytes = ((3 * p.N * 4 + 127) / 128) * 128;                // bias | wsum | ln_g cache
+  const int budget = kSmemLimit - kHeader - pbytes;
   const long wbytes = (long)nk * s.stageB * (p.N / p.NT);           // every N tile
   s.resident = (p.w_image_stride == 0 && wbytes + s.stageA <= budget) ? 1 : 0;
   s.offA = kHeader;
@@ -77,7 +80,8 @@ __host__ inline SmemPlan plan_smem(const idiff_gemm_params& p) {
     s.SA = sa > kMaxSA ? kMaxSA : sa;
     s.SB = 0;
     s.offB = s.offA + s.SA * s.stageA;
-    s.total = s.offB + (int)wbytes;
+    s.offP = s.offB + (int)wbytes;
+    s.total = s.offP + pbytes;
   } else {
     s.SA = 2;
     if (2 * s.stageA + 2 * s.stageB > budget) s.SA = 1;
@@ -88,7 +92,8 @@ __host__ inline SmemPlan plan_smem(const idiff_gemm_params& p) {
     s.SB = sb;
     if (s.SA == 2 && s.SA * s.stageA + s.SB * s.stageB + s.stageA <= budget) s.SA = 3;   // spare room: 3rd A stage
     s.offB = s.offA + s.SA * s.stageA;
-    s.total = s.offB + s.SB * s.stageB;
+    s.offP = s.offB + s.SB * s.stageB;
+    s.total = s.offP + pbytes;
   }
   return s;
 }
@@ -97,7 +102,7 @@ int watchdog_conv(int clear) { return watchdog_read_tu(clear); }
 
 struct KArgs {
   idiff_gemm_params p;
-  int SA, SB, resident, offA, offB;
+  int SA, SB, resident, offA, offB, offP;
   int tiles_x, tiles_y, ntiles_n, total_items;
 };
 
@@ -112,28 +117,60 @@ __device__ unsigned long long g_prof[16];
 
 IDIFF_DEVINL float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-struct Item {
-  int b, tile_in_img, oy0, ox0, nt;
+// Work-item iterator: item -> (n tile, tile x, tile y, image), advanced by the grid stride with carries only
+// (the three integer divisions happen once per thread, not once per item).
+struct ItemIter {
+  int item, nt, tx, ty, b;            // current item
+  int s_nt, s_tx, s_ty, s_b;          // decomposition of the stride (gridDim.x)
+  int ntiles_n, tiles_x, tiles_y, total;
+  IDIFF_DEVINL void init(const KArgs& a, int first, int stride) {
+    ntiles_n = a.ntiles_n; tiles_x = a.tiles_x; tiles_y = a.tiles_y; total = a.total_items;
+    item = first;
+    decompose(first, nt, tx, ty, b);
+    decompose(stride, s_nt, s_tx, s_ty, s_b);
+  }
+  IDIFF_DEVINL void decompose(int v, int& n, int& x, int& y, int& bb) const {
+    n = v % ntiles_n;                                  // N tiles of one pixel tile are adjacent: A patch hits L2
+    int m = v / ntiles_n;
+    x = m % tiles_x;
+    m /= tiles_x;
+    y = m % tiles_y;
+    bb = m / tiles_y;
+  }
+  IDIFF_DEVINL bool valid() const { return item < total; }
+  IDIFF_DEVINL void next() {
+    item += s_nt + ntiles_n * (s_tx + tiles_x * (s_ty + tiles_y * s_b));   // == gridDim.x (kept as a sum of parts)
+    nt += s_nt;
+    int c = nt >= ntiles_n;
+    nt -= c ? ntiles_n : 0;
+    tx += s_tx + c;
+    c = tx >= tiles_x;
+    tx -= c ? tiles_x : 0;
+    ty += s_ty + c;
+    c = ty >= tiles_y;
+    ty -= c ? tiles_y : 0;
+    b += s_b + c;
+  }
+  IDIFF_DEVINL int tile_in_img() const { return ty * tiles_x + tx; }
+  IDIFF_DEVINL int oy0() const { return ty * TILE_H; }
+  IDIFF_DEVINL int ox0() const { return tx * TILE_W; }
 };
-IDIFF_DEVINL Item decode_item(const KArgs& a, int item) {
-  Item it;
-  it.nt = item % a.ntiles_n;                         // N tiles of one pixel tile are adjacent: A patch hits L2
-  const int mt = item / a.ntiles_n;
-  const int tpi = a.tiles_x * a.tiles_y;
-  it.b = mt / tpi;
-  it.tile_in_img = mt - it.b * tpi;
-  const int ty = it.tile_in_img / a.tiles_x;
-  it.oy0 = ty * TILE_H;
-  it.ox0 = (it.tile_in_img - ty * a.tiles_x) * TILE_W;
-  return it;
-}
 
-// v[0..31] op= per-column parameters p[n..n+32) (8 broadcast float4 loads, 4 temporaries live at a time)
+// ring position with explicit wrap (no modulo: stays in the uniform datapath for the single-issuer warps)
+struct Ring {
+  int slot, phase, n;
+  IDIFF_DEVINL void init(int stages) { slot = 0; phase = 0; n = stages; }
+  IDIFF_DEVINL void advance() {
+    if (++slot == n) { slot = 0; phase ^= 1; }
+  }
+};
+
+// v[0..31] op= per-column parameters p[n..n+32) staged in shared memory (8 broadcast LDS.128)
 template <typename F>
 IDIFF_DEVINL void for_cols32(const float* __restrict__ p, float* v, F f) {
 #pragma unroll
   for (int q4 = 0; q4 < 8; ++q4) {
-    const float4 t = ldg4(p + q4 * 4);
+    const float4 t = *reinterpret_cast<const float4*>(p + q4 * 4);   // shared memory, warp-broadcast
     v[q4 * 4] = f(v[q4 * 4], t.x);
     v[q4 * 4 + 1] = f(v[q4 * 4 + 1], t.y);
     v[q4 * 4 + 2] = f(v[q4 * 4 + 2], t.z);
@@ -204,11 +241,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
   // Register re-balancing (per warpgroup).  The CTA owns 640 x 96 = 61440 registers (launch bounds); `inc` can
   // only draw on what `dec` released inside the CTA, so the targets must satisfy
-  //   256*EPI + 256*LOADER + 128*OTHER <= 61440   ->   136 / 80 / 40  (= 60416).
-  static_assert(256 * 136 + 256 * 80 + 128 * 40 <= kThreads * 96, "setmaxnreg budget exceeds the CTA's registers");
+  //   256*EPI + 256*LOADER + 128*OTHER <= 61440   ->   128 / 88 / 40  (= 60416).
+  static_assert(256 * 128 + 256 * 88 + 128 * 40 <= kThreads * 96, "setmaxnreg budget exceeds the CTA's registers");
   if (warp >= kWarpB) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  else if (warp >= kEpiWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+  else if (warp >= kEpiWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
 
   if (warp < kEpiWarps) {
     // ============================== epilogue (TMEM -> registers -> global) ====================
@@ -220,14 +257,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const __nv_bfloat16* res1 = reinterpret_cast<const __nv_bfloat16*>(p.res1);
     const bool gn = p.gn_groups > 0;                              // requires NT == N: exactly 8 groups per tile
     const float invN = 1.f / (float)p.N;
+    // per-layer column parameters staged once per CTA: [bias | wsum | ln_g], N floats each
+    float* pcache = reinterpret_cast<float*>(smem + a.offP);
+    for (int i = tid; i < p.N; i += kEpiThreads) {
+      pcache[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+      pcache[p.N + i] = p.wsum ? __ldg(p.wsum + i) : 0.f;
+      pcache[2 * p.N + i] = p.ln_g ? __ldg(p.ln_g + i) : 1.f;
+    }
+    const bool img_params = p.bias_img != nullptr || p.res0_scale != nullptr;
+    float* pimg_all = reinterpret_cast<float*>(smem + kOffImg);   // [2 items][bias_img | res0_scale | res0_shift][256]
+    epi_bar();
 
     long long pacc9 = 0, pacc10 = 0;
     int it_local = 0;
-    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x, ++it_local) {
-      const Item it = decode_item(a, item);
+    ItemIter it;
+    for (it.init(a, blockIdx.x, gridDim.x); it.valid(); it.next(), ++it_local) {
       const int b = it.b, n0 = it.nt * NT;
       const int ab = it_local & 1;
-      const int oy = it.oy0 + ti, ox = it.ox0 + tj;
+      const int oy = it.oy0() + ti, ox = it.ox0() + tj;
       const bool valid = (oy < p.H) && (ox < p.W);
       const size_t m = ((size_t)b * p.H + (valid ? oy : 0)) * p.W + (valid ? ox : 0);   // clamped: loads stay legal
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * NT);
@@ -238,11 +285,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         mean_in = __ldg(p.row_stats + 2 * m);
         rstd_in = __ldg(p.row_stats + 2 * m + 1);
       }
+      // per-image column parameters of this item's N tile -> shared memory (before waiting for the accumulator)
+      float* pimg = pimg_all + ab * (3 * 256);
+      if (img_params) {
+        if (tid < NT) {
+          const size_t gi = (size_t)b * p.N + n0 + tid;
+          pimg[tid] = p.bias_img ? __ldg(p.bias_img + gi) : 0.f;
+          pimg[256 + tid] = p.res0_scale ? __ldg(p.res0_scale + gi) : 1.f;
+          pimg[512 + tid] = p.res0_scale ? __ldg(p.res0_shift + gi) : 0.f;
+        }
+        epi_bar();
+      }
       // accumulator chunk -> value after LayerNorm fold + biases (32 columns starting at global column n)
       auto apply_base = [&](float* v, int n) {
-        if (p.row_stats) for_cols32(p.wsum + n, v, [&](float x, float c) { return (x - mean_in * c) * rstd_in; });
-        if (p.bias) for_cols32(p.bias + n, v, [](float x, float c) { return x + c; });
-        if (p.bias_img) for_cols32(p.bias_img + (size_t)b * p.N + n, v, [](float x, float c) { return x + c; });
+        if (p.row_stats) for_cols32(pcache + p.N + n, v, [&](float x, float c) { return (x - mean_in * c) * rstd_in; });
+        if (p.bias) for_cols32(pcache + n, v, [](float x, float c) { return x + c; });
+        if (p.bias_img) for_cols32(pimg + (n - n0), v, [](float x, float c) { return x + c; });
       };
       auto add_residuals = [&](float* v, int n) {
         if (res0) {
@@ -251,8 +309,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           for (int q4 = 0; q4 < 4; ++q4)
             unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(res0 + m * p.N + n + q4 * 8)), rr + q4 * 8);
           if (p.res0_scale) {                                       // residual enters as silu(GN(y)) (ResBlock tail)
-            for_cols32(p.res0_scale + (size_t)b * p.N + n, rr, [](float x, float c) { return x * c; });
-            for_cols32(p.res0_shift + (size_t)b * p.N + n, rr, [](float x, float c) { return silu_fast(x + c); });
+            for_cols32(pimg + 256 + (n - n0), rr, [](float x, float c) { return x * c; });
+            for_cols32(pimg + 512 + (n - n0), rr, [](float x, float c) { return silu_fast(x + c); });
           }
 #pragma unroll
           for (int q = 0; q < 32; ++q) v[q] += rr[q];
@@ -317,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           tmem_ld32(taddr + cc * 32, v);
           if (j == NCH - 1) release_tmem();
           apply_base(v, n0 + cc * 32);
-          for_cols32(p.ln_g + n0 + cc * 32, v, [&](float x, float c) { return (x - mean) * rstd * c; });
+          for_cols32(pcache + 2 * p.N + n0 + cc * 32, v, [&](float x, float c) { return (x - mean) * rstd * c; });
           add_residuals(v, n0 + cc * 32);
           if (p.out_row_stats) {
 #pragma unroll
@@ -395,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             float sum = 0.f;
 #pragma unroll
             for (int q = 0; q < 4; ++q) sum += redi[(h * 4 + q) * 8 + l * 2 + st];
-            p.gn_partial[(((size_t)b * tiles_per_img + it.tile_in_img) * 8 + Gi) * 2 + st] = sum;
+            p.gn_partial[(((size_t)b * tiles_per_img + it.tile_in_img()) * 8 + Gi) * 2 + st] = sum;
           }
         }
       }
@@ -422,7 +480,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int Hin = p.H * G::S, Win = p.W * G::S;                     // virtual (possibly upsampled) input extent
     const int Hs = p.up0 ? (Hin >> 1) : Hin, Ws = p.up0 ? (Win >> 1) : Win;
     const bool affine = p.a_scale != nullptr;
-    int a_iter = 0;                                                   // running (item, chunk) counter -> ring slot
     long long pacc2 = 0, pacc3 = 0, pacc4 = 0;
     // patch coordinates of this thread's pixels: identical for every tile and chunk
     int pv[BATCH], pu[BATCH], pslot[BATCH];
@@ -436,66 +493,141 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       pslot[i] = in_patch ? G::slot(pv[i], pu[i]) : -1;
     }
 
-    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-      const Item it = decode_item(a, item);
-      const int b = it.b;
-      const int iy0 = it.oy0 * G::S - G::PAD, ix0 = it.ox0 * G::S - G::PAD;
-      for (int ch = 0; ch < nchunks; ++ch, ++a_iter) {
-        const int sa = a_iter % a.SA;
+    // per-stage source description (stage = one 64-channel chunk of one item)
+    struct Src {
+      const __nv_bfloat16* base;     // image b, channel offset applied
+      const __nv_bfloat16* origin;   // base + patch origin (iy0, ix0) -- only meaningful for interior tiles
+      int Cs, iy0, ix0, b, ch;
+      bool interior;                 // whole patch inside the image and no upsampling: pre-computed offsets apply
+    };
+    auto describe = [&](const ItemIter& it, int ch) {
+      Src sd;
+      const bool from0 = (ch << 6) < p.cin0;
+      const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(from0 ? p.src0 : p.src1);
+      sd.Cs = from0 ? (p.src0_ld ? p.src0_ld : p.cin0) : (p.src1_ld ? p.src1_ld : p.cin1);
+      const int coff = (from0 ? (ch << 6) : ((ch << 6) - p.cin0)) + c8 * 8;
+      sd.base = src + (size_t)it.b * Hs * Ws * sd.Cs + coff;
+      sd.iy0 = it.oy0() * G::S - G::PAD;
+      sd.ix0 = it.ox0() * G::S - G::PAD;
+      sd.interior = !p.up0 && sd.iy0 >= 0 && sd.ix0 >= 0 && sd.iy0 + G::PR <= Hin && sd.ix0 + G::PC <= Win;
+      sd.origin = sd.base + ((long long)sd.iy0 * Ws + sd.ix0) * sd.Cs;
+      sd.b = it.b;
+      sd.ch = ch;
+      return sd;
+    };
+    // branch-free batch: every load is issued from an always-valid address; returns the in-image mask
+    const uint32_t patch_mask = [&] {
+      uint32_t m = 0;
+#pragma unroll
+      for (int i = 0; i < BATCH; ++i) m |= pslot[i] >= 0 ? (1u << i) : 0u;
+      return m;
+    }();
+    auto issue = [&](const Src& sd, uint4* q) -> uint32_t {
+      if (sd.interior) {
+        // (pv*Ws + pu)*Cs relative to the patch origin: one 32-bit multiply-add per vector, no bounds tests
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i) {
+          const int rel = (pslot[i] >= 0) ? (pv[i] * Ws + pu[i]) * sd.Cs : 0;
+          q[i] = __ldg(reinterpret_cast<const uint4*>(sd.origin + rel));
+        }
+        return patch_mask;
+      }
+      uint32_t mask = 0;
+#pragma unroll
+      for (int i = 0; i < BATCH; ++i) {
+        const int iy = sd.iy0 + pv[i], ix = sd.ix0 + pu[i];
+        const bool ok = pslot[i] >= 0 && iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
+        const int sy = p.up0 ? (iy >> 1) : iy, sx = p.up0 ? (ix >> 1) : ix;
+        const size_t off = ok ? ((size_t)sy * Ws + sx) * sd.Cs : 0;
+        mask |= ok ? (1u << i) : 0u;
+        q[i] = __ldg(reinterpret_cast<const uint4*>(sd.base + off));
+      }
+      return mask;
+    };
+    // affine with the 0.5 of silu(y) = h*tanh(h) + h, h = y/2, folded in when SiLU follows
+    const float half_if_silu = p.a_silu ? 0.5f : 1.0f;
+    auto load_affine = [&](const Src& sd, float* sc, float* sh) {
+      const float* ps = p.a_scale + (size_t)sd.b * cin + (sd.ch << 6) + c8 * 8;
+      const float* pt = p.a_shift + (size_t)sd.b * cin + (sd.ch << 6) + c8 * 8;
+      const float4 s0 = ldg4(ps), s1 = ldg4(ps + 4), t0 = ldg4(pt), t1 = ldg4(pt + 4);
+      sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+      sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { sc[e] *= half_if_silu; sh[e] *= half_if_silu; }
+    };
+    auto transform_store = [&](uint8_t* stage, const uint4& qv, bool ok, int slot, const float* sc, const float* sh) {
+      if (slot < 0) return;
+      uint4 o = ok ? qv : make_uint4(0u, 0u, 0u, 0u);
+      if (affine && ok) {
+        float f[8];
+        unpack_bf16x8(qv, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float h = fmaf(f[e], sc[e], sh[e]);
+          f[e] = p.a_silu ? fmaf(h, tanh_fast(h), h) : h;
+        }
+        o = pack_bf16x8(f);
+      }
+      *reinterpret_cast<uint4*>(stage + slot * 16) = o;
+    };
+
+    Ring ra;
+    ra.init(a.SA);
+    bool first_lap = true;
+    ItemIter it;
+    it.init(a, blockIdx.x, gridDim.x);
+    if (kSmall) {
+      // Software pipeline: the loads of stage s+1 are in flight while stage s is transformed and stored.
+      int ch = 0;
+      bool have = it.valid();
+      uint4 qn[BATCH];
+      uint32_t mask_n = 0;
+      Src cur;
+      if (have) {
+        cur = describe(it, ch);
+        mask_n = issue(cur, qn);
+      }
+      while (have) {
+        uint4 qc[BATCH];
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i) qc[i] = qn[i];
+        const uint32_t mask_c = mask_n;
+        const Src now = cur;
+        // advance to the next stage and put its loads in flight
+        if (++ch == nchunks) { ch = 0; it.next(); }
+        have = it.valid();
         long long tp = PROF_T();
-        if (a_iter >= a.SA) mbar_wait(&emptyA[sa], (((a_iter / a.SA) & 1) ^ 1), 101);
+        if (have) {
+          cur = describe(it, ch);
+          mask_n = issue(cur, qn);
+        }
+        PROF_ADD(3, tp);
+        tp = PROF_T();
+        if (!first_lap) mbar_wait(&emptyA[ra.slot], ra.phase ^ 1, 101);
         PROF_ADD(2, tp);
         tp = PROF_T();
-        uint8_t* stage = smem + a.offA + sa * G::STAGE + c8 * G::LBO;
-
-        const bool from0 = (ch << 6) < p.cin0;
-        const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(from0 ? p.src0 : p.src1);
-        const int Cs = from0 ? (p.src0_ld ? p.src0_ld : p.cin0) : (p.src1_ld ? p.src1_ld : p.cin1);
-        const int coff = (from0 ? (ch << 6) : ((ch << 6) - p.cin0)) + c8 * 8;
-        const __nv_bfloat16* src_b = src + (size_t)b * Hs * Ws * Cs + coff;
-
+        uint8_t* stage = smem + a.offA + ra.slot * G::STAGE + c8 * G::LBO;
         float sc[8], sh[8];
-        if (affine) {
-          const float* ps = p.a_scale + (size_t)b * cin + (ch << 6) + c8 * 8;
-          const float* pt = p.a_shift + (size_t)b * cin + (ch << 6) + c8 * 8;
-          const float4 s0 = ldg4(ps), s1 = ldg4(ps + 4), t0 = ldg4(pt), t1 = ldg4(pt + 4);
-          sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-          sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
-        }
-        auto transform_store = [&](const uint4& qv, bool ok, int slot) {
-          if (slot < 0) return;
-          uint4 o = ok ? qv : make_uint4(0u, 0u, 0u, 0u);
-          if (affine && ok) {
-            float f[8];
-            unpack_bf16x8(qv, f);
+        if (affine) load_affine(now, sc, sh);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float y = fmaf(f[e], sc[e], sh[e]);
-              f[e] = p.a_silu ? silu_fast(y) : y;
-            }
-            o = pack_bf16x8(f);
-          }
-          *reinterpret_cast<uint4*>(stage + slot * 16) = o;
-        };
-
-        if (kSmall) {
-          // one branch-free batch with the pre-computed coordinates: all loads in flight together
-          uint4 q[BATCH];
-          bool inb[BATCH];
-#pragma unroll
-          for (int i = 0; i < BATCH; ++i) {
-            const int iy = iy0 + pv[i], ix = ix0 + pu[i];
-            const bool ok = pslot[i] >= 0 && iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
-            const int sy = p.up0 ? (iy >> 1) : iy, sx = p.up0 ? (ix >> 1) : ix;
-            const size_t off = ok ? ((size_t)sy * Ws + sx) * Cs : 0;
-            inb[i] = ok;
-            q[i] = __ldg(reinterpret_cast<const uint4*>(src_b + off));
-          }
-          PROF_ADD(3, tp);
+        for (int i = 0; i < BATCH; ++i) transform_store(stage, qc[i], (mask_c >> i) & 1u, pslot[i], sc, sh);
+        fence_proxy_async_smem();
+        mbar_arrive(&fullA[ra.slot]);
+        ra.advance();
+        if (ra.slot == 0) first_lap = false;
+        PROF_ADD(4, tp);
+      }
+    } else {
+      for (; it.valid(); it.next()) {
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const Src sd = describe(it, ch);
+          long long tp = PROF_T();
+          if (!first_lap) mbar_wait(&emptyA[ra.slot], ra.phase ^ 1, 101);
+          PROF_ADD(2, tp);
           tp = PROF_T();
-#pragma unroll
-          for (int i = 0; i < BATCH; ++i) transform_store(q[i], inb[i], pslot[i]);
-        } else {
+          uint8_t* stage = smem + a.offA + ra.slot * G::STAGE + c8 * G::LBO;
+          float sc[8], sh[8];
+          if (affine) load_affine(sd, sc, sh);
           for (int px0 = prow; px0 < G::NSLOT; px0 += SWEEP * BATCH) {
             uint4 q[BATCH];
             int slot[BATCH];
@@ -507,20 +639,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               const int pxc = in_patch ? px : 0;
               const int v = pxc / G::PC, u = pxc - v * G::PC;
               slot[i] = in_patch ? G::slot(v, u) : -1;
-              const int iy = iy0 + v, ix = ix0 + u;
+              const int iy = sd.iy0 + v, ix = sd.ix0 + u;
               const bool ok = in_patch && iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
               const int sy = p.up0 ? (iy >> 1) : iy, sx = p.up0 ? (ix >> 1) : ix;
-              const size_t off = ok ? ((size_t)sy * Ws + sx) * Cs : 0;
+              const size_t off = ok ? ((size_t)sy * Ws + sx) * sd.Cs : 0;
               inb[i] = ok;
-              q[i] = __ldg(reinterpret_cast<const uint4*>(src_b + off));
+              q[i] = __ldg(reinterpret_cast<const uint4*>(sd.base + off));
             }
 #pragma unroll
-            for (int i = 0; i < BATCH; ++i) transform_store(q[i], inb[i], slot[i]);
+            for (int i = 0; i < BATCH; ++i) transform_store(stage, q[i], inb[i], slot[i], sc, sh);
           }
+          fence_proxy_async_smem();
+          mbar_arrive(&fullA[ra.slot]);
+          ra.advance();
+          if (ra.slot == 0) first_lap = false;
+          PROF_ADD(4, tp);
         }
-        fence_proxy_async_smem();
-        mbar_arrive(&fullA[sa]);
-        PROF_ADD(4, tp);
       }
     }
     if (prof && ltid == 0) { g_prof[2] = pacc2; g_prof[3] = pacc3; g_prof[4] = pacc4; }
@@ -539,17 +673,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
       }
     } else {
-      int b_iter = 0;
-      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-        const Item it = decode_item(a, item);
+      Ring rb;
+      rb.init(a.SB);
+      bool first_lap = true;
+      ItemIter it;
+      for (it.init(a, blockIdx.x, gridDim.x); it.valid(); it.next()) {
         const uint8_t* wbase = w0 + 2 * ((size_t)it.b * p.w_image_stride + (size_t)it.nt * nk * NT * 64);
-        for (int ks = 0; ks < nk; ++ks, ++b_iter) {
-          const int sb = b_iter % a.SB;
-          if (b_iter >= a.SB) mbar_wait(&emptyB[sb], (((b_iter / a.SB) & 1) ^ 1), 103);
+        for (int ks = 0; ks < nk; ++ks) {
+          if (!first_lap) mbar_wait(&emptyB[rb.slot], rb.phase ^ 1, 103);
           if (leader) {
-            mbar_arrive_expect_tx(&fullB[sb], (uint32_t)stageB);
-            bulk_g2s(smem + a.offB + sb * stageB, wbase + (size_t)ks * stageB, (uint32_t)stageB, &fullB[sb]);
+            mbar_arrive_expect_tx(&fullB[rb.slot], (uint32_t)stageB);
+            bulk_g2s(smem + a.offB + rb.slot * stageB, wbase + (size_t)ks * stageB, (uint32_t)stageB, &fullB[rb.slot]);
           }
+          rb.advance();
+          if (rb.slot == 0) first_lap = false;
         }
       }
     }
@@ -561,41 +698,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     constexpr uint32_t lboB = NT * 16, sboB = 128;
     const uint32_t a_hi = umma_desc_hi(G::SBO), b_hi = umma_desc_hi(sboB);
     const uint32_t a0 = smem_u32(smem + a.offA), b0 = smem_u32(smem + a.offB);
-    int a_iter = 0, b_iter = 0, it_local = 0;
     long long pacc5 = 0, pacc6 = 0, pacc7 = 0, pacc8 = 0;
     if (a.resident) {
       mbar_wait(wres_bar, 0, 106);
       tc_fence_after();
     }
-    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x, ++it_local) {
-      const int nt = item % a.ntiles_n;
-      const int ab = it_local & 1;
+    // all indices below advance with compare-and-wrap only (uniform datapath; no modulo, no division)
+    Ring ra, rb;
+    ra.init(a.SA);
+    rb.init(a.SB > 0 ? a.SB : 1);
+    int ab = 0, acc_phase = 0, items_done = 0, nt = blockIdx.x % a.ntiles_n;
+    const int nt_step = gridDim.x % a.ntiles_n;
+    const uint32_t res_item_stride = (uint32_t)((nk * stageB) >> 4);          // descriptor units per N tile
+    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
       long long tp = PROF_T();
-      if (it_local >= 2) mbar_wait(&tmem_empty[ab], (((it_local >> 1) & 1) ^ 1), 107);
+      if (items_done >= 2) mbar_wait(&tmem_empty[ab], acc_phase ^ 1, 107);
       tc_fence_after();
       PROF_ADD(5, tp);
       const uint32_t tacc = tmem_u + (uint32_t)(ab * NT);
-      for (int ch = 0; ch < nchunks; ++ch, ++a_iter) {
-        const int sa = a_iter % a.SA;
+      uint32_t b_res = umma_desc_lo(b0, lboB) + (uint32_t)nt * res_item_stride;  // resident: this N tile, chunk 0
+      for (int ch = 0; ch < nchunks; ++ch) {
         tp = PROF_T();
-        mbar_wait(&fullA[sa], (a_iter / a.SA) & 1, 104);
+        mbar_wait(&fullA[ra.slot], ra.phase, 104);
         tc_fence_after();
         PROF_ADD(6, tp);
-        const uint32_t a_lo0 = umma_desc_lo(a0 + sa * G::STAGE, G::LBO);
-        const uint32_t b_res0 = umma_desc_lo(b0 + (uint32_t)((nt * nk + ch * ntaps) * stageB), lboB);
+        const uint32_t a_lo0 = umma_desc_lo(a0 + ra.slot * G::STAGE, G::LBO);
 #pragma unroll
         for (int tap = 0; tap < ntaps; ++tap) {
           uint32_t b_lo0;
-          int sb = 0;
           if (a.resident) {
-            b_lo0 = b_res0 + (uint32_t)((tap * stageB) >> 4);
+            b_lo0 = b_res + (uint32_t)((tap * stageB) >> 4);
           } else {
-            sb = b_iter % a.SB;
             tp = PROF_T();
-            mbar_wait(&fullB[sb], (b_iter / a.SB) & 1, 105);
+            mbar_wait(&fullB[rb.slot], rb.phase, 105);
             tc_fence_after();
             PROF_ADD(7, tp);
-            b_lo0 = umma_desc_lo(b0 + sb * stageB, lboB);
+            b_lo0 = umma_desc_lo(b0 + rb.slot * stageB, lboB);
           }
           tp = PROF_T();
           const int tapslot = G::slot(tap / KS, tap % KS);                       // compile time
@@ -606,15 +744,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               const uint32_t b_lo = b_lo0 + (uint32_t)((kk * 2 * lboB) >> 4);
               umma_bf16_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, (ch | tap | kk) != 0 ? 1u : 0u);
             }
-            if (!a.resident) umma_commit(&emptyB[sb]);
+            if (!a.resident) umma_commit(&emptyB[rb.slot]);
           }
-          if (!a.resident) ++b_iter;
+          if (!a.resident) rb.advance();
           PROF_ADD(8, tp);
         }
-        if (leader) umma_commit(&emptyA[sa]);
+        if (leader) umma_commit(&emptyA[ra.slot]);
+        ra.advance();
+        b_res += (uint32_t)((ntaps * stageB) >> 4);
       }
       if (leader) umma_commit(&tmem_full[ab]);
       __syncwarp();
+      ++items_done;
+      ab ^= 1;
+      if (ab == 0) acc_phase ^= 1;
+      nt += nt_step;
+      if (nt >= a.ntiles_n) nt -= a.ntiles_n;
     }
     if (prof && leader) { g_prof[5] = pacc5; g_prof[6] = pacc6; g_prof[7] = pacc7; g_prof[8] = pacc8; }
   }
@@ -712,7 +857,7 @@ int idiff_conv_gemm(const idiff_gemm_params* pp, void* stream) {
   KArgs a;
   a.p = *pp;
   const SmemPlan s = plan_smem(*pp);
-  a.SA = s.SA; a.SB = s.SB; a.resident = s.resident; a.offA = s.offA; a.offB = s.offB;
+  a.SA = s.SA; a.SB = s.SB; a.resident = s.resident; a.offA = s.offA; a.offB = s.offB; a.offP = s.offP;
   a.tiles_x = (pp->W + TILE_W - 1) / TILE_W;
   a.tiles_y = (pp->H + TILE_H - 1) / TILE_H;
   a.ntiles_n = pp->N / pp->NT;
