@@ -40,29 +40,34 @@ IDIFF_DEVINL void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or ~`ns` elapse,
-// so waiting warps do not burn issue slots that the working warps need.
-IDIFF_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t ns = 200000u) {
+IDIFF_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }
-// Bounded wait (~1 s).  `code` identifies the call site in the watchdog word.  The clock and the watchdog word
-// are only looked at when a (sleeping) try comes back empty, i.e. at most every ~0.2 ms.
+// Bounded wait (~1 s).  `code` identifies the call site in the watchdog word.  Waiting warps back off with
+// nanosleep so they do not steal issue slots from the working warps; the clock / watchdog word are read only
+// every 256 polls.
 IDIFF_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity, int code) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
+  uint64_t t0 = 0;
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (*((volatile int*)&g_watchdog) != 0) return;
-    if (globaltimer_ns() - t0 > 1000000000ull) {
-      atomicCAS(&g_watchdog, 0, code);
-      return;
+    __nanosleep(64);
+    if ((++polls & 255u) == 0) {
+      if (*((volatile int*)&g_watchdog) != 0) return;
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 1000000000ull) {
+        atomicCAS(&g_watchdog, 0, code);
+        return;
+      }
     }
   }
 }

@@ -112,8 +112,13 @@ struct KArgs {
 //  5 mma: wait tmem_empty  6 mma: wait fullA       7 mma: wait fullB   8 mma: issue
 //  9 epi: wait tmem_full  10 epi: work
 __device__ unsigned long long g_prof[16];
+#ifdef IDIFF_PROF
 #define PROF_T() (prof ? clock64() : 0ll)
 #define PROF_ADD(i, t0) do { if (prof) { pacc##i += clock64() - (t0); } } while (0)
+#else                                   // production build: the hooks compile to nothing
+#define PROF_T() 0ll
+#define PROF_ADD(i, t0) do { (void)(t0); } while (0)
+#endif
 
 IDIFF_DEVINL float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -217,7 +222,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   float2* xch = reinterpret_cast<float2*>(smem + kOffXch);   // [2 kinds][2 halves][128 rows]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef IDIFF_PROF
   const bool prof = p.reserved0 != 0 && blockIdx.x == 0;
+#else
+  constexpr bool prof = false;
+#endif
   const long long t_kernel = prof ? clock64() : 0ll;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
   const int cin = p.cin0 + p.cin1, nchunks = cin >> 6;
@@ -609,8 +618,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         uint8_t* stage = smem + a.offA + ra.slot * G::STAGE + c8 * G::LBO;
         float sc[8], sh[8];
         if (affine) load_affine(now, sc, sh);
+        if (mask_c == patch_mask) {                      // whole patch inside the image: no zero-fill selects
 #pragma unroll
-        for (int i = 0; i < BATCH; ++i) transform_store(stage, qc[i], (mask_c >> i) & 1u, pslot[i], sc, sh);
+          for (int i = 0; i < BATCH; ++i) transform_store(stage, qc[i], true, pslot[i], sc, sh);
+        } else {
+#pragma unroll
+          for (int i = 0; i < BATCH; ++i) transform_store(stage, qc[i], (mask_c >> i) & 1u, pslot[i], sc, sh);
+        }
         fence_proxy_async_smem();
         mbar_arrive(&fullA[ra.slot]);
         ra.advance();

@@ -1,4 +1,7 @@
-"""Per-role cycle breakdown of conv_gemm on the bench's dominant layer shapes (CTA 0 counters)."""
+"""Per-role cycle breakdown of conv_gemm on the bench's dominant layer shapes (CTA 0 counters).
+
+Needs the profiling build:  make -C instancediff_b200/csrc OBJDIR=build_prof OUT=../libidiff_prof.so EXTRA=-DIDIFF_PROF
+and IDIFF_LIB_PATH=instancediff_b200/libidiff_prof.so (without it the counters read 0 and only the timings are valid)."""
 import ctypes
 import math
 import os
