@@ -96,6 +96,13 @@ class ClockSampler:
         return out
 
 
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -118,8 +125,7 @@ def cpu_reference_rate(n_images, n_sde_steps, threads=None):
     full T=100 sampling extrapolated from `n_sde_steps` steps on `n_images` images."""
     from oracle import irsde_oracle as O
     from oracle.unet_oracle import make_oracle_unet
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or host_threads())        # torchrun exports OMP_NUM_THREADS=1: claim the cores
     net = make_oracle_unet(seed=1)
     s = O.make_schedule(0.4, T_STEPS, schedule="cosine", eps=0.01)
     mu, ctx = synthetic_inputs(n_images, 1, False)
@@ -139,7 +145,7 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    cores = torch.get_num_threads()
+    cores = host_threads()
     n_img, n_steps = 2, 1                                   # bounded sample per bench step
     rates = []
     for i in range(args.warmup + args.steps):
@@ -292,7 +298,7 @@ def run_cuda(args):
         "forward_ms_sum_of_kernels": fwd_ms,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = torch.get_num_threads()
+        cores = host_threads()
         val, dt = cpu_reference_rate(1, args.cpu_steps)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{args.cpu_steps} of {T_STEPS} SDE steps on 1 image @{RES}x{RES} fp32 (BASELINE config 1), "

@@ -177,149 +177,172 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
 }
 
 // =====================================================================================================
-// Linear attention context.
+// Linear attention context on tensor cores.
+//   ctx[h][d][e] = sum_n softmax_n(k)[d,n] v[e,n] / HW
+// With the exact per-channel maximum m[d] (pre-pass), E = exp(k - m) in (0,1]:
+//   G = E^T [v | 1]   (128 k-channels x 144 columns; fp32, accumulated over pixels by tcgen05.mma)
+//   ctx[h][d][e] = G[h*32+d][h*32+e] / (G[h*32+d][128] * HW)
+// Both operands are MN-major views of the [8-channel plane][pixel][8] tiles the loaders write (the same
+// layout/descriptor roles the self-attention V operand uses).  The Gram matrix over all 4 heads is computed at
+// once (M = 128) and only the 4 diagonal 32x32 blocks are kept.
 // =====================================================================================================
-constexpr int LA_ROWS = 256;                 // rows staged per pass
-constexpr int LA_CHUNK = 4096;               // rows per CTA
-constexpr int LA_PART = 32 + 32 + 1024;      // floats per partial: m[32], S[32], ctx[32][32]
+constexpr int LA_CHUNK = 4096;                               // pixels per CTA
+constexpr int LA_SUB = 128;                                  // pixels per MMA batch (8 x K16)
+constexpr int LA_PLANE = LA_SUB * 16 + 32;                   // bytes between 8-channel planes
+constexpr int LA_OFF_E = 0;                                  // [16 planes] E tile  (A, MN-major: k-channels x pixels)
+constexpr int LA_OFF_V = LA_OFF_E + 16 * LA_PLANE;           // [18 planes] [v | 1] (B, MN-major: 144 columns x pixels)
+constexpr int LA_OFF_MAX = LA_OFF_V + 18 * LA_PLANE;         // [128] floats
+constexpr int LA_OFF_BAR = LA_OFF_MAX + 512;
+constexpr int LA_SMEM = LA_OFF_BAR + 64;
+constexpr int LA_NCOL = 144;
+constexpr int LA_PART = 128 * 33;                            // floats per (image, chunk): diagonal block + row sum
 
-// grid = (nchunk, 4 heads, B), block = 256
+// per-(image, chunk) column maxima of k: grid = (nchunk, B), block = 256
 __global__ void __launch_bounds__(256)
-linattn_partial_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ part, int HW) {
-  extern __shared__ __align__(16) float lsm[];
-  float* ks = lsm;                          // [LA_ROWS][32]
-  float* vs = lsm + LA_ROWS * 32;           // [LA_ROWS][32]
-  float* red = vs + LA_ROWS * 32;           // [8][32]
-  float* mcur = red + 256;                  // [32]
-  float* fac = mcur + 32;                   // [32] rescale factor of the running sums
-  const int tid = threadIdx.x, chunk = blockIdx.x, h = blockIdx.y, b = blockIdx.z, nchunk = gridDim.x;
-  const int row_begin = chunk * LA_CHUNK, row_end = min(HW, row_begin + LA_CHUNK);
-  const __nv_bfloat16* kb = qkv + (size_t)b * HW * 384 + 128 + h * 32;
-  const __nv_bfloat16* vb = kb + 128;
-
-  const int sub = tid >> 6, tt = tid & 63, d0 = (tt >> 3) * 4, e0 = (tt & 7) * 4;
-  float acc[4][4];
+linattn_kmax_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ pmax, int HW) {
+  __shared__ float red[16][128];
+  const int tid = threadIdx.x, chunk = blockIdx.x, b = blockIdx.y, nchunk = gridDim.x;
+  const int c8 = tid & 15, rg = tid >> 4;
+  const int r0 = chunk * LA_CHUNK, r1 = min(HW, r0 + LA_CHUNK);
+  const __nv_bfloat16* kb = qkv + (size_t)b * HW * 384 + 128 + c8 * 8;
+  float mx[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int e = 0; e < 8; ++e) mx[e] = -INFINITY;
+  for (int r = r0 + rg; r < r1; r += 16) {
+    float f[8];
+    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(kb + (size_t)r * 384)), f);
 #pragma unroll
-    for (int jx = 0; jx < 4; ++jx) acc[i][jx] = 0.f;
-  float s_run = 0.f;                         // thread tid<32 keeps S[d = tid]
-  if (tid < 32) mcur[tid] = -INFINITY;
-  __syncthreads();
-
-  for (int r0 = row_begin; r0 < row_end; r0 += LA_ROWS) {
-    const int nr = min(LA_ROWS, row_end - r0);
-    // stage k and v rows as fp32 (rows beyond nr: k = -inf so exp() = 0, v = 0)
-    for (int i = tid; i < LA_ROWS * 4; i += 256) {
-      const int r = i >> 2, c8 = i & 3;
-      float fk[8], fv[8];
-      if (r < nr) {
-        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(kb + (size_t)(r0 + r) * 384 + c8 * 8)), fk);
-        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(vb + (size_t)(r0 + r) * 384 + c8 * 8)), fv);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { fk[e] = -INFINITY; fv[e] = 0.f; }
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { ks[r * 32 + c8 * 8 + e] = fk[e]; vs[r * 32 + c8 * 8 + e] = fv[e]; }
-    }
-    __syncthreads();
-    // column max of this pass
-    {
-      const int d = tid & 31, rg = tid >> 5;
-      float mx = -INFINITY;
-      for (int r = rg; r < LA_ROWS; r += 8) mx = fmaxf(mx, ks[r * 32 + d]);
-      red[rg * 32 + d] = mx;
-    }
-    __syncthreads();
-    if (tid < 32) {
-      float mx = red[tid];
-#pragma unroll
-      for (int g = 1; g < 8; ++g) mx = fmaxf(mx, red[g * 32 + tid]);
-      const float m_old = mcur[tid], m_new = fmaxf(m_old, mx);
-      fac[tid] = __expf(m_old - m_new);      // 0 on the first pass
-      mcur[tid] = m_new;
-    }
-    __syncthreads();
-    // exponentiate in place, column sums
-    {
-      const int d = tid & 31, rg = tid >> 5;
-      const float m = mcur[d];
-      float s = 0.f;
-      for (int r = rg; r < LA_ROWS; r += 8) {
-        const float ev = __expf(ks[r * 32 + d] - m);
-        ks[r * 32 + d] = ev;
-        s += ev;
-      }
-      red[rg * 32 + d] = s;
-    }
-    __syncthreads();
-    if (tid < 32) {
-      float s = 0.f;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) s += red[g * 32 + tid];
-      s_run = s_run * fac[tid] + s;
-    }
-    // rescale the running context, then accumulate this pass (each 64-thread group owns 64 rows)
-    {
-      const float4 f4 = *reinterpret_cast<const float4*>(fac + d0);
-      const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int jx = 0; jx < 4; ++jx) acc[i][jx] *= ff[i];
-      for (int r = sub * 64; r < sub * 64 + 64; ++r) {
-        const float4 k4 = *reinterpret_cast<const float4*>(ks + r * 32 + d0);
-        const float4 v4 = *reinterpret_cast<const float4*>(vs + r * 32 + e0);
-        const float kk[4] = {k4.x, k4.y, k4.z, k4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int jx = 0; jx < 4; ++jx) acc[i][jx] = fmaf(kk[i], vv[jx], acc[i][jx]);
-      }
-    }
-    __syncthreads();
+    for (int e = 0; e < 8; ++e) mx[e] = fmaxf(mx[e], f[e]);
   }
-  // reduce the 4 row-subsets through shared memory (re-use ks) and emit the partial
-  float* cred = ks;                          // [4][1024]
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int jx = 0; jx < 4; ++jx) cred[sub * 1024 + (d0 + i) * 32 + e0 + jx] = acc[i][jx];
+  for (int e = 0; e < 8; ++e) red[rg][c8 * 8 + e] = mx[e];
   __syncthreads();
-  float* dst = part + (((size_t)b * 4 + h) * nchunk + chunk) * LA_PART;
-  for (int i = tid; i < 1024; i += 256) dst[64 + i] = cred[i] + cred[1024 + i] + cred[2048 + i] + cred[3072 + i];
-  if (tid < 32) {
-    dst[tid] = mcur[tid];
-    dst[32 + tid] = s_run;
+  if (tid < 128) {
+    float m = red[0][tid];
+#pragma unroll
+    for (int g = 1; g < 16; ++g) m = fmaxf(m, red[g][tid]);
+    pmax[((size_t)b * nchunk + chunk) * 128 + tid] = m;
   }
 }
 
-// grid = (4 heads, B), block = 256: merge partials -> ctx_h (smem), then
+// grid = (nchunk, B), block = 256
+__global__ void __launch_bounds__(256)
+linattn_gram_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ pmax, float* __restrict__ part,
+                    int HW, int dbg) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  float* kmax = reinterpret_cast<float*>(sm + LA_OFF_MAX);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + LA_OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, chunk = blockIdx.x, b = blockIdx.y, nchunk = gridDim.x;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (tid < 128) {                                           // exact channel maximum over the whole image
+    float m = -INFINITY;
+    for (int c = 0; c < nchunk; ++c) m = fmaxf(m, pmax[((size_t)b * nchunk + c) * 128 + tid]);
+    kmax[tid] = m;
+  }
+  // the two constant "ones" planes of B (columns 128..143): written once
+  for (int i = tid; i < 2 * LA_SUB; i += 256) {
+    const uint32_t one2 = 0x3F803F80u;                        // bf16(1.0) x2
+    *reinterpret_cast<uint4*>(sm + LA_OFF_V + (16 + (i >> 7)) * LA_PLANE + (i & 127) * 16) = make_uint4(one2, one2, one2, one2);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const bool leader = (warp == 0) && elect_one();
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+  const uint32_t smem0 = smem_u32(sm);
+  const bool sw = (dbg & 8) != 0;
+  const uint32_t lbo = sw ? LA_PLANE : 128, sbo = sw ? 128 : LA_PLANE;    // MN-major: LBO = 8-pixel group pitch
+  const uint32_t e_lo = umma_desc_lo(smem0 + LA_OFF_E, lbo), v_lo = umma_desc_lo(smem0 + LA_OFF_V, lbo);
+  const uint32_t hi = umma_desc_hi(sbo);
+  const uint32_t idesc = umma_idesc_bf16_ex(128, LA_NCOL, 1, 1);
+
+  const int c8 = tid & 15, rg = tid >> 4;                     // 16 pixels per sweep, 8 sweeps per sub-block
+  float mloc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) mloc[e] = kmax[c8 * 8 + e];
+  const __nv_bfloat16* kb = qkv + (size_t)b * HW * 384 + 128 + c8 * 8;
+  const __nv_bfloat16* vb = kb + 128;
+  const int r_begin = chunk * LA_CHUNK, r_end = min(HW, r_begin + LA_CHUNK);
+  int it = 0;
+  for (int r0 = r_begin; r0 < r_end; r0 += LA_SUB, ++it) {
+    uint4 qk[8], qv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                              // branch-free: clamped row
+      const int r = r0 + rg + 16 * i;
+      const int rc = r < r_end ? r : r_end - 1;
+      qk[i] = __ldg(reinterpret_cast<const uint4*>(kb + (size_t)rc * 384));
+      qv[i] = __ldg(reinterpret_cast<const uint4*>(vb + (size_t)rc * 384));
+    }
+    if (it > 0) mbar_wait(bar, (it - 1) & 1, 301);             // previous MMAs finished reading the tiles
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int px = rg + 16 * i;
+      const bool ok = r0 + px < r_end;
+      float f[8];
+      unpack_bf16x8(qk[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = ok ? __expf(f[e] - mloc[e]) : 0.f;
+      *reinterpret_cast<uint4*>(sm + LA_OFF_E + c8 * LA_PLANE + px * 16) = pack_bf16x8(f);
+      *reinterpret_cast<uint4*>(sm + LA_OFF_V + c8 * LA_PLANE + px * 16) = ok ? qv[i] : make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (leader) {
+#pragma unroll
+        for (int kk = 0; kk < LA_SUB / 16; ++kk)              // K = 16 pixels per MMA: advance by two 8-pixel groups
+          umma_bf16_lohi(tmem_u, e_lo + ((kk * 256) >> 4), hi, v_lo + ((kk * 256) >> 4), hi, idesc, (it | kk) != 0 ? 1u : 0u);
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+  }
+  mbar_wait(bar, (it - 1) & 1, 302);
+  tc_fence_after();
+  // epilogue: warps 0-3 own TMEM lanes (k-channel rows); keep the head-diagonal 32 columns + the row sum
+  if (warp < 4) {
+    const int d = warp * 32 + (tid & 31);                     // k channel = row
+    float* dst = part + ((size_t)b * nchunk + chunk) * LA_PART + (size_t)d * 33;
+    float v[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(warp * 32), v);   // head h = warp: columns h*32..
+#pragma unroll
+    for (int e = 0; e < 32; ++e) dst[e] = v[e];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 128u, v);                    // columns 128..159 (128 = row sum)
+    dst[32] = v[0];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// grid = (4 heads, B), block = 256: sum the per-chunk Gram blocks, normalise, then
 // Weff[c][h*32+d] = sum_e Wout[c][h*32+e] ctx[h][d][e]   (the columns of this head)
 __global__ void __launch_bounds__(256)
 linattn_merge_kernel(const float* __restrict__ part, int nchunk, const float* __restrict__ w_out,
                      __nv_bfloat16* __restrict__ weff, int HW, int C) {
   __shared__ float ctx[32 * 33];
-  __shared__ float mfin[32], sfin[32];
+  __shared__ float ssum[32];
   const int tid = threadIdx.x, h = blockIdx.x, b = blockIdx.y;
-  const float* p0 = part + ((size_t)b * 4 + h) * nchunk * LA_PART;
-  if (tid < 32) {
-    float m = -INFINITY;
-    for (int c = 0; c < nchunk; ++c) m = fmaxf(m, p0[(size_t)c * LA_PART + tid]);
-    float s = 0.f;
-    for (int c = 0; c < nchunk; ++c) s += p0[(size_t)c * LA_PART + 32 + tid] * __expf(p0[(size_t)c * LA_PART + tid] - m);
-    mfin[tid] = m;
-    sfin[tid] = s;
+  const float* p0 = part + (size_t)b * nchunk * LA_PART + (size_t)(h * 32) * 33;
+  for (int i = tid; i < 32 * 33; i += 256) {                  // rows d = 0..31 of this head, 33 values each
+    float acc = 0.f;
+    for (int c = 0; c < nchunk; ++c) acc += p0[(size_t)c * LA_PART + i];
+    ctx[i] = acc;
   }
   __syncthreads();
-  for (int i = tid; i < 1024; i += 256) {
-    const int d = i >> 5, e = i & 31;
-    const float m = mfin[d];
-    float acc = 0.f;
-    for (int c = 0; c < nchunk; ++c) acc += p0[(size_t)c * LA_PART + 64 + i] * __expf(p0[(size_t)c * LA_PART + d] - m);
-    ctx[d * 33 + e] = acc / (sfin[d] * (float)HW);           // softmax normaliser and v / (h*w)
-  }
+  if (tid < 32) ssum[tid] = 1.f / (ctx[tid * 33 + 32] * (float)HW);   // softmax normaliser and v / (h*w)
   __syncthreads();
   __nv_bfloat16* wdst = weff + (size_t)b * C * 128;
   for (int i = tid; i < C * 32; i += 256) {
@@ -329,6 +352,7 @@ linattn_merge_kernel(const float* __restrict__ part, int nchunk, const float* __
     float acc = 0.f;
 #pragma unroll 8
     for (int e = 0; e < 32; ++e) acc = fmaf(__ldg(wr + e), cr[e], acc);
+    acc *= ssum[d];
     // packed B-operand layout of conv_gemm (NT = C, two 64-wide K stages)
     const int ks = kc >> 6, kin = kc & 63;
     wdst[(size_t)ks * C * 64 + (kin >> 3) * (C * 8) + c * 8 + (kin & 7)] = __float2bfloat16_rn(acc);
@@ -362,25 +386,29 @@ int idiff_set_debug_flags(int flags) {
 
 size_t idiff_linattn_scratch_floats(int B, int HW) {
   const size_t nchunk = (size_t)(HW + LA_CHUNK - 1) / LA_CHUNK;
-  return (size_t)B * 4 * nchunk * LA_PART;
+  return (size_t)B * nchunk * (LA_PART + 128);               // Gram partials + per-chunk channel maxima
 }
 
 int idiff_linattn_context(const void* qkv, const float* w_out, void* weff_packed, float* scratch, int B, int HW,
                           int C, void* stream) {
   IDIFF_REQUIRE(qkv && w_out && weff_packed && scratch && B > 0 && HW > 0, "linattn_context: bad arguments");
   IDIFF_REQUIRE(C == 64 || C == 128 || C == 256, "linattn_context: C must be 64/128/256");
+  IDIFF_REQUIRE(aligned16(qkv), "linattn_context: 16 B alignment");
   const int nchunk = (HW + LA_CHUNK - 1) / LA_CHUNK;
-  const int smem = (2 * LA_ROWS * 32 + 256 + 64) * (int)sizeof(float);
+  float* part = scratch;
+  float* pmax = scratch + (size_t)B * nchunk * LA_PART;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(linattn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(linattn_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LA_SMEM);
     if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "linattn attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  dim3 grid((unsigned)nchunk, 4u, (unsigned)B);
-  linattn_partial_kernel<<<grid, 256, smem, as_stream(stream)>>>((const __nv_bfloat16*)qkv, scratch, HW);
-  if (int rc = check_launch("linattn_partial")) return rc;
-  linattn_merge_kernel<<<dim3(4, (unsigned)B), 256, 0, as_stream(stream)>>>(scratch, nchunk, w_out,
+  dim3 grid((unsigned)nchunk, (unsigned)B);
+  linattn_kmax_kernel<<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)qkv, pmax, HW);
+  if (int rc = check_launch("linattn_kmax")) return rc;
+  linattn_gram_kernel<<<grid, 256, LA_SMEM, as_stream(stream)>>>((const __nv_bfloat16*)qkv, pmax, part, HW, g_debug_flags);
+  if (int rc = check_launch("linattn_gram")) return rc;
+  linattn_merge_kernel<<<dim3(4, (unsigned)B), 256, 0, as_stream(stream)>>>(part, nchunk, w_out,
                                                                             (__nv_bfloat16*)weff_packed, HW, C);
   return check_launch("linattn_merge");
 }

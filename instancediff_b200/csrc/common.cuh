@@ -143,6 +143,11 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N, int b_mn_major
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Same, with selectable majors for both operands (1 = MN-major).
+__host__ __device__ inline uint32_t umma_idesc_bf16_ex(int M, int N, int a_mn_major, int b_mn_major) {
+  return umma_idesc_bf16(M, N, b_mn_major) | ((uint32_t)(a_mn_major & 1) << 15);
+}
+
 // Exactly one lane of a converged warp gets `true`.  The MMA / bulk-copy issuing warps stay warp-uniform and
 // predicate only the issue on this, so descriptors live in uniform registers (no R2UR waterfall).
 IDIFF_DEVINL bool elect_one() {

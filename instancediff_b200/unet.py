@@ -507,7 +507,7 @@ class _Plan:
         args = (_ptr(qkv.t), _ptr(to["w_f32"]), _ptr(weff), _ptr(scratch), B, H * W, Cc)
         self.ops.append(lambda s: check(L.idiff_linattn_context(*args, s), "linattn_context"))
         self.op_info.append(("linattn_context", 2.0 * 2 * B * H * W * 128 * 32, f"C{Cc} @{H}x{W}"))
-        self.n_launch += 2
+        self.n_launch += 3
         out = self.act(H, W, Cc)
         entry = dict(N=Cc, NT=Cc, w=weff, bias=to["bias"])
         self.gemm(qkv, None, entry, out, k=1, cin0=128, src0_ld=384, w_image_stride=Cc * 128, epi=EPI_LN_OUT,
