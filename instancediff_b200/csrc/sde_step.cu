@@ -76,20 +76,38 @@ sde_step_kernel(float* __restrict__ xo, const float* __restrict__ x, const float
   const bool noise = philox || z != nullptr;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   if (kVec) {
+    // two independent float4 items per thread per sweep: all loads are issued before the arithmetic
     const size_t n4 = n >> 2;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-      const float4 xv = __ldcs(reinterpret_cast<const float4*>(x) + i);
-      const float4 ev = __ldcs(reinterpret_cast<const float4*>(eps) + i);
-      const float4 mv = mu ? __ldg(reinterpret_cast<const float4*>(mu) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (philox) zv = philox_normal4(seed, (elem_offset >> 2) + i, c.step);
-      else if (z) zv = __ldcs(reinterpret_cast<const float4*>(z) + i);
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+      const size_t i1 = i0 + stride;
+      const bool two = i1 < n4;
+      const size_t j1 = two ? i1 : i0;
+      const float4 xa = __ldcs(reinterpret_cast<const float4*>(x) + i0), xb = __ldcs(reinterpret_cast<const float4*>(x) + j1);
+      const float4 ea = __ldcs(reinterpret_cast<const float4*>(eps) + i0), eb = __ldcs(reinterpret_cast<const float4*>(eps) + j1);
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 ma = mu ? __ldg(reinterpret_cast<const float4*>(mu) + i0) : zero;
+      const float4 mb = mu ? __ldg(reinterpret_cast<const float4*>(mu) + j1) : zero;
+      float4 za = zero, zb = zero;
+      if (philox) {
+        za = philox_normal4(seed, (elem_offset >> 2) + i0, c.step);
+        zb = philox_normal4(seed, (elem_offset >> 2) + j1, c.step);
+      } else if (z) {
+        za = __ldcs(reinterpret_cast<const float4*>(z) + i0);
+        zb = __ldcs(reinterpret_cast<const float4*>(z) + j1);
+      }
       float4 o;
-      o.x = sde_update(xv.x, ev.x, mv.x, zv.x, c, is_score, noise);
-      o.y = sde_update(xv.y, ev.y, mv.y, zv.y, c, is_score, noise);
-      o.z = sde_update(xv.z, ev.z, mv.z, zv.z, c, is_score, noise);
-      o.w = sde_update(xv.w, ev.w, mv.w, zv.w, c, is_score, noise);
-      reinterpret_cast<float4*>(xo)[i] = o;
+      o.x = sde_update(xa.x, ea.x, ma.x, za.x, c, is_score, noise);
+      o.y = sde_update(xa.y, ea.y, ma.y, za.y, c, is_score, noise);
+      o.z = sde_update(xa.z, ea.z, ma.z, za.z, c, is_score, noise);
+      o.w = sde_update(xa.w, ea.w, ma.w, za.w, c, is_score, noise);
+      reinterpret_cast<float4*>(xo)[i0] = o;
+      if (two) {
+        o.x = sde_update(xb.x, eb.x, mb.x, zb.x, c, is_score, noise);
+        o.y = sde_update(xb.y, eb.y, mb.y, zb.y, c, is_score, noise);
+        o.z = sde_update(xb.z, eb.z, mb.z, zb.z, c, is_score, noise);
+        o.w = sde_update(xb.w, eb.w, mb.w, zb.w, c, is_score, noise);
+        reinterpret_cast<float4*>(xo)[i1] = o;
+      }
     }
   } else {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -169,7 +187,12 @@ int idiff_sde_step(float* x_out, const float* x, const float* eps, const float* 
   const bool vec = (n % 4 == 0) && aligned16(x_out) && aligned16(x) && aligned16(eps) && (!mu || aligned16(mu)) &&
                    (!z || aligned16(z)) && (elem_offset % 4 == 0);
   if (vec) {
-    sde_step_kernel<true><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
+    // exactly two float4 items per thread when the tensor is large enough: one balanced wave (<= 8 CTAs per SM)
+    const size_t n4 = n / 4;
+    size_t blocks = (n4 + 511) / 512;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    sde_step_kernel<true><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
         x_out, x, eps, mu, z, coef, input_is_score, use_philox, seed, elem_offset, n);
   } else {
     sde_step_kernel<false><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(

@@ -550,12 +550,13 @@ class _Plan:
         self.named[prefix] = out
         return out
 
-    def conv(self, name, x: _Act, cout, k=3, stride=1, up=0) -> _Act:
+    def conv(self, name, x: _Act, cout, k=3, stride=1, up=0, res0=None) -> _Act:
         H = x.H // 2 if stride == 2 else (x.H * 2 if up else x.H)
         W = x.W // 2 if stride == 2 else (x.W * 2 if up else x.W)
         out = self.act(H, W, cout)
-        self.gemm(x, None, self.net.pk[name], out, k=k, stride=stride, up=up)
-        self.named[name[:-5] if name.endswith(".conv") else name] = out
+        self.gemm(x, None, self.net.pk[name], out, k=k, stride=stride, up=up, res0=res0)
+        key = name[:-5] if name.endswith(".conv") else name
+        self.named[key + "+init_conv" if res0 is not None else key] = out
         return out
 
     # ---- whole network
@@ -597,16 +598,16 @@ class _Plan:
             h = self.resblock(f"ups.{i}.0", h, skips.pop(), do)
             h = self.resblock(f"ups.{i}.1", h, skips.pop(), do, want_stats=not last)
             h = self.spatial_attn(f"ups.{i}.2", h) if last else self.linear_attn(f"ups.{i}.2", h)
-            h = self.conv(f"ups.{i}.3.conv", h, di, k=3, up=1) if lvl > 0 else self.conv(f"ups.{i}.3", h, di, k=3)
-        xa = self.act(H, W, nf)
-        a_add = (_ptr(h.t), _ptr(x_first.t), _ptr(xa.t), None, 1e-5, B * H * W, nf)
-        self.ops.append(lambda s: check(L.idiff_add_rows(*a_add, s), "add_rows"))
-        self.op_info.append(("add_rows", 0.0, f"C{nf} @{H}x{W}"))
+            if lvl > 0:
+                h = self.conv(f"ups.{i}.3.conv", h, di, k=3, up=1)
+            else:       # last up conv: its epilogue also adds the stem output (x + x_ of the final concat, App. A)
+                h = self.conv(f"ups.{i}.3", h, di, k=3, res0=x_first.t)
+        xa = h
         h = self.resblock("final_res", xa, x_first, nf)
         a_head = (_ptr(h.t), _ptr(pk["final_conv"]["w"]), pk["final_conv"]["bias"], _ptr(self.eps), B, H, W, nf)
         self.ops.append(lambda s: check(L.idiff_head_conv3(*a_head, s), "head_conv3"))
         self.op_info.append(("head_conv3", 2.0 * B * H * W * nf * 9, f"@{H}x{W}"))
-        self.n_launch += 2
+        self.n_launch += 1
 
     def run_timed(self, xt, cond, t_scalar, reps=3):
         """Instrumented replay (bench/profiling): CUDA events around every launch on the launching stream.
