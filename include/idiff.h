@@ -87,7 +87,10 @@ int idiff_debug_read_prof(unsigned long long* out16_host);
  * One CTA computes a 16x8-pixel x NT-channel tile: the input patch (with halo) is staged once
  * per 64-channel chunk in shared memory in the UMMA no-swizzle K-major layout and re-used by every
  * filter tap through shifted matrix descriptors; weights stream in by bulk TMA; fp32
- * accumulators live in TMEM. */
+ * accumulators live in TMEM; the output (and, for NT == 64, the residuals) move as bulk-tensor
+ * TMA copies through 128B-swizzled staging tiles.
+ * Built combinations: 3x3 {no transform | affine+SiLU}, 4x4/s2 {no transform}, 1x1 {any transform};
+ * QSOFTMAX needs NT == 128, GEGLU NT == 256, LN_OUT NT == N; anything else -> IDIFF_ERR_UNSUPPORTED. */
 typedef struct idiff_gemm_params {
   /* geometry (OUTPUT grid) */
   int32_t B, H, W;          /* output pixels */
@@ -121,7 +124,7 @@ typedef struct idiff_gemm_params {
   const float* res0_shift;
   const float* ln_g;        /* IDIFF_EPI_LN_OUT: gain [N] */
   void* out;                /* bf16 */
-  float* gn_partial;        /* [B][tiles_per_image][gn_groups][2] */
+  float* gn_partial;        /* [B][idiff_conv_gemm_gn_rows(H,W)][gn_groups][2]: one row per 8x4-pixel quarter tile */
   float* out_row_stats;     /* [B*H*W][2] LayerNorm stats of the stored row (needs NT == N) */
   float qscale;             /* IDIFF_EPI_QSOFTMAX: multiplier after the softmax */
   float ln_eps;
@@ -139,6 +142,9 @@ int idiff_conv_gemm(const idiff_gemm_params* p, void* stream);
 int idiff_sizeof_gemm_params(void);
 /* shared memory the kernel will request for these params (bytes), or negative status */
 int idiff_conv_gemm_smem_bytes(const idiff_gemm_params* p);
+/* rows of GroupNorm partial sums idiff_conv_gemm writes per image for an H x W output (the `ntile`
+ * argument of idiff_gn_finalize): 4 per 16x8-pixel tile, one per epilogue warp. */
+int idiff_conv_gemm_gn_rows(int H, int W);
 
 /* Plain CUDA-core convolution over the same params subset (ksize, stride, cin0/cin1, up0, a_*,
  * bias, PLAIN epilogue, fp32 weights [N][k][k][cin]).  Used for validation of the tensor-core path. */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "idiff_conv_gemm": (C.c_int, [C.POINTER(GemmParams), c_ptr]),
     "idiff_sizeof_gemm_params": (C.c_int, []),
     "idiff_conv_gemm_smem_bytes": (C.c_int, [C.POINTER(GemmParams)]),
+    "idiff_conv_gemm_gn_rows": (C.c_int, [C.c_int, C.c_int]),
     "idiff_conv_ref": (C.c_int, [C.POINTER(GemmParams), c_ptr, c_ptr, c_ptr]),
     "idiff_stem_conv7": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr]),
     "idiff_head_conv3": (C.c_int, [c_ptr, c_ptr, C.c_float, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr]),

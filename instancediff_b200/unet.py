@@ -447,7 +447,8 @@ class _Plan:
                 p.bias_img = buf.data_ptr()
 
     def tiles(self, H, W):
-        return ((H + TILE_H - 1) // TILE_H) * ((W + TILE_W - 1) // TILE_W)
+        """rows of GroupNorm partial sums per image written by idiff_conv_gemm (one per epilogue warp and tile)"""
+        return self.L.idiff_conv_gemm_gn_rows(H, W)
 
     def gn_finalize(self, partial, ntile, norm, C, G, count, eps, t_off=None, tag="gn"):
         sc = self.tmp(tag + "_sc", (self.B, C), torch.float32)

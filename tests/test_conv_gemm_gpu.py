@@ -106,8 +106,10 @@ def test_cuda_core_reference_agrees():
 def test_groupnorm_partials():
     from instancediff_b200 import ops
     B, H, W, N = 2, 32, 24, 128
-    tiles = ((H + 15) // 16) * ((W + 7) // 8)
-    part = torch.zeros(B, tiles, 8, 2, device="cuda")
+    from instancediff_b200 import _lib
+    rows = _lib.lib().idiff_conv_gemm_gn_rows(H, W)
+    assert rows == 4 * ((H + 15) // 16) * ((W + 7) // 8)
+    part = torch.zeros(B, rows, 8, 2, device="cuda")
     out, ref, _ = _run(B, H, W, 64, 0, N, 3, gn_groups=8, gn_partial=part)
     s = part.sum(dim=1)                                       # [B, 8, 2]
     r = ref.reshape(B, H * W, 8, N // 8)
@@ -199,11 +201,14 @@ def test_epilogues_qsoftmax_geglu_lnout_residuals():
     assert rel_err(out, ref) <= TOL, describe(out, ref, "ln_out")
 
 
-def test_resblock_tail_in_shortcut_epilogue_and_image_bias():
-    """1x1 shortcut conv whose epilogue adds silu(GN(y2)) (res0 affine) and a per-image bias."""
+@pytest.mark.parametrize("N,H,W", [(128, 16, 16), (64, 32, 24), (256, 8, 8)])
+def test_resblock_tail_in_shortcut_epilogue_and_image_bias(N, H, W):
+    """1x1 shortcut conv whose epilogue adds silu(GN(y2)) (res0 affine), a second residual and a per-image bias.
+    N = 64 takes the TMA residual path (ragged tiles: zero-filled loads, clipped stores), N = 256 stages the
+    per-image columns with a 128-thread epilogue group."""
     from instancediff_b200 import ops
     g = torch.Generator().manual_seed(7)
-    B, H, W, N = 2, 16, 16, 128
+    B = 2
     y2 = rand_act(B, H, W, N, g)
     sc2 = (torch.rand(B, N, generator=g) + 0.5).cuda()
     sh2 = (torch.rand(B, N, generator=g) - 0.5).cuda()

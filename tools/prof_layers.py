@@ -30,7 +30,7 @@ def run(B, H, W, cin0, cin1, N, k, NT=None, affine=False, gn=False, res=False, s
     if affine:
         kw.update(a_scale=torch.ones(B, cin, device=dev), a_shift=torch.zeros(B, cin, device=dev), a_silu=1)
     if gn:
-        tiles = ((H + 15) // 16) * ((W + 7) // 8)
+        tiles = 4 * ((H + 15) // 16) * ((W + 7) // 8)
         kw.update(gn_groups=8, gn_partial=torch.zeros(B, tiles, 8, 2, device=dev))
     if res:
         kw.update(res0=torch.randn(B, H, W, N, generator=g).to(dev).to(torch.bfloat16),
@@ -51,7 +51,8 @@ def run(B, H, W, cin0, cin1, N, k, NT=None, affine=False, gn=False, res=False, s
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     buf = (ctypes.c_ulonglong * 16)()
-    _lib.check(_lib.lib().idiff_debug_read_prof(buf))
+    if _lib.lib().idiff_debug_read_prof(buf) != 0:      # production build: no counters, timings only
+        buf = (ctypes.c_ulonglong * 16)()
     v = list(buf)
     items = max(v[1], 1)
     flops = 2.0 * B * H * W * N * cin * k * k

@@ -23,4 +23,10 @@ if "a" in which:
     P.run(B, 256, 256, 64, 0, 64, 3, gn=True, affine=True, label="3x3 64->64 affine+silu+gn")
 if "b" in which:
     P.run(B, 256, 256, 64, 64, 64, 1, res=True, label="1x1 128->64 shortcut+tail")
+if "c" in which:
+    P.run(B, 256, 256, 64, 0, 64, 3, gn=True, label="3x3 64->64 plain+gn")
+if "d" in which:
+    P.run(B, 256, 256, 64, 0, 384, 1, NT=128, stats=True, epi=1, label="1x1 64->384 qkv (ln-fold, qsoftmax)")
+if "e" in which:
+    P.run(B, 256, 256, 64, 64, 64, 3, gn=True, label="3x3 128->64 concat+gn")
 torch.cuda.synchronize()
