@@ -248,7 +248,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int r = quarter * 32 + lane, ti = r >> 3, tj = r & 7;   // accumulator row = tile pixel
     constexpr int NC = NT / 32;                                   // 32-column chunks per row
     constexpr int CPG = NT / 8;                                   // channels per GroupNorm group (NT == N)
-    constexpr int GN_BATCH = CPG / 8;                             // chunks that complete 4 groups
     constexpr bool kTmaRes = NT == 64;
     constexpr bool kTmaOut = EPI != IDIFF_EPI_GEGLU;
     __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
@@ -412,10 +411,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       tp = PROF_T();
 
       float o1 = 0.f, o2 = 0.f;
+      // The chunk loops below stay ROLLED: one copy of the per-chunk code keeps the epilogue's instruction
+      // footprint inside the instruction cache it shares with the loader and MMA warps.
       if (EPI == IDIFF_EPI_LN_OUT) {
         // pass 1: LayerNorm statistics over the whole row (NT == N), thread-local
         float s1 = 0.f, s2 = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int cc = 0; cc < NC; ++cc) {
           float v[32];
           tmem_ld32(taddr + cc * 32, v);
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
         const float mean = s1 * invN, var = fmaxf(s2 * invN - mean * mean, 0.f);
         const float rstd = rsqrtf(var + p.ln_eps);
-#pragma unroll
+#pragma unroll 1
         for (int cc = 0; cc < NC; ++cc) {
           float v[32];
           tmem_ld32(taddr + cc * 32, v);
@@ -440,10 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           store32(v, cc);
         }
       } else {
-        float gl[8];                                      // GroupNorm: [group slot 0..3][sum, sum of squares]
-#pragma unroll
-        for (int i = 0; i < 8; ++i) gl[i] = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int cc = 0; cc < NC; ++cc) {
           float v[32];
           tmem_ld32(taddr + cc * 32, v);
@@ -452,26 +450,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           apply_base(v, ncol0);
 
           if (EPI == IDIFF_EPI_PLAIN && gn) {
-            // partial sums of the conv output (bias included) over this warp's 32 pixels.  8-column block g8 of
-            // chunk cc belongs to group (cc*32 + g8*8) / CPG; four groups are reduced and written together.
-            if (valid) {
+            // partial sums of the conv output (bias included) over this warp's 32 pixels: the four 8-column
+            // blocks of the chunk are reduced over the warp together (lane L ends up with value L >> 2 =
+            // block*2 + {sum, sum of squares}); blocks of the same group (CPG = 16: pairs, CPG = 32: all four)
+            // are then folded and one lane per (group, statistic) writes.
+            float gl[8];
 #pragma unroll
-              for (int g8 = 0; g8 < 4; ++g8) {
-                const int slot = ((cc * 32 + g8 * 8) / CPG) & 3;
-                float s1 = 0.f, s2 = 0.f;
+            for (int g8 = 0; g8 < 4; ++g8) {
+              float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) { const float x = v[g8 * 8 + q]; s1 += x; s2 = fmaf(x, x, s2); }
-                gl[2 * slot] += s1;
-                gl[2 * slot + 1] += s2;
-              }
+              for (int q = 0; q < 8; ++q) { const float x = v[g8 * 8 + q]; s1 += x; s2 = fmaf(x, x, s2); }
+              gl[2 * g8] = valid ? s1 : 0.f;
+              gl[2 * g8 + 1] = valid ? s2 : 0.f;
             }
-            if ((cc + 1) % GN_BATCH == 0) {
-              const float tot = warp_reduce8(gl, lane);   // lane L: warp total of value index L >> 2
-              const int gbase = ((cc * 32) / CPG) & ~3;   // first group of this batch
-              if ((lane & 3) == 0)
-                p.gn_partial[(((size_t)b * tiles_per_img + it.tile_in_img()) * 4 + quarter) * 16 + gbase * 2 + (lane >> 2)] = tot;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) gl[i] = 0.f;
+            float tot = warp_reduce8(gl, lane);
+            if (CPG >= 16) tot += __shfl_xor_sync(0xffffffffu, tot, 8);
+            if (CPG >= 32) tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+            const int g8 = lane >> 3, st = (lane >> 2) & 1;
+            constexpr int BPG = CPG / 8;                  // 8-column blocks per group
+            if ((lane & 3) == 0 && (g8 % BPG) == 0) {
+              const int grp_idx = (cc * 32) / CPG + g8 / BPG;
+              p.gn_partial[(((size_t)b * tiles_per_img + it.tile_in_img()) * 4 + quarter) * 16 + grp_idx * 2 + st] = tot;
             }
           }
 
@@ -479,10 +478,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             float mx = v[0];
 #pragma unroll
             for (int q = 1; q < 32; ++q) mx = fmaxf(mx, v[q]);
-            float s = 0.f;
+            float sm = 0.f;
 #pragma unroll
-            for (int q = 0; q < 32; ++q) { v[q] = __expf(v[q] - mx); s += v[q]; }
-            const float inv = p.qscale / s;
+            for (int q = 0; q < 32; ++q) { v[q] = __expf(v[q] - mx); sm += v[q]; }
+            const float inv = p.qscale / sm;
 #pragma unroll
             for (int q = 0; q < 32; ++q) v[q] *= inv;
             store32(v, cc);
@@ -662,18 +661,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         PROF_ADD(2, tp);
         tp = PROF_T();
         uint8_t* stage = smem + a.offA + ra.slot * G::STAGE + c8 * G::LBO;
-        if (mask_c == act_mask) {                          // whole patch inside the image
+        // one copy of the transform: border pixels are transformed too (their registers hold zeros) and then
+        // replaced by the zero padding, which applies AFTER the activation
 #pragma unroll
-          for (int i = 0; i < BATCH; ++i) {
-            const bool on = (SWEEP * (i + 1) <= G::NSLOT) || ((act_mask >> i) & 1u);
-            if (on) *reinterpret_cast<uint4*>(stage + soff[i]) = transform(qc[i]);
-          }
-        } else {                                           // zero padding is applied AFTER the transform
-#pragma unroll
-          for (int i = 0; i < BATCH; ++i) {
-            if ((act_mask >> i) & 1u)
-              *reinterpret_cast<uint4*>(stage + soff[i]) =
-                  ((mask_c >> i) & 1u) ? transform(qc[i]) : make_uint4(0u, 0u, 0u, 0u);
+        for (int i = 0; i < BATCH; ++i) {
+          const bool on = (SWEEP * (i + 1) <= G::NSLOT) || ((act_mask >> i) & 1u);
+          if (on) {
+            uint4 o = transform(qc[i]);
+            if (!((mask_c >> i) & 1u)) o = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(stage + soff[i]) = o;
           }
         }
         publish();
@@ -780,41 +776,65 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       PROF_ADD(5, tp);
       const uint32_t tacc = tmem_u + (uint32_t)(ab * NT);
       uint32_t b_res = umma_desc_lo(b0, lboB) + (uint32_t)nt * res_item_stride;  // resident: this N tile, chunk 0
+      uint32_t accum = 0;
+#pragma unroll 1
       for (int ch = 0; ch < nchunks; ++ch) {
         tp = PROF_T();
         mbar_wait(&fullA[ra.slot], ra.phase, 104);
         tc_fence_after();
         PROF_ADD(6, tp);
-        const uint32_t a_lo0 = umma_desc_lo(a0 + ra.slot * G::STAGE, G::LBO);
-#pragma unroll
-        for (int tap = 0; tap < ntaps; ++tap) {
-          uint32_t b_lo0;
-          if (a.resident) {
-            b_lo0 = b_res + (uint32_t)((tap * stageB) >> 4);
-          } else {
-            tp = PROF_T();
-            mbar_wait(&fullB[rb.slot], rb.phase, 105);
-            tc_fence_after();
-            PROF_ADD(7, tp);
-            b_lo0 = umma_desc_lo(b0 + rb.slot * stageB, lboB);
-          }
+        // Tap loops stay ROLLED (one copy of the 4-MMA body): the tap's patch offset advances by one pixel per
+        // dx and by the rest of the patch row per dy -- adds on uniform registers only.
+        uint32_t a_lo = umma_desc_lo(a0 + ra.slot * G::STAGE, G::LBO);
+        if (a.resident) {
           tp = PROF_T();
-          const int tapslot = G::slot(tap / KS, tap % KS);                       // compile time
-          if (leader) {
+          uint32_t b_lo = b_res;
+#pragma unroll 1
+          for (int dy = 0; dy < KS; ++dy) {
+#pragma unroll 1
+            for (int dx = 0; dx < KS; ++dx) {
+              if (leader) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint32_t a_lo = a_lo0 + (uint32_t)((tapslot * 16 + kk * 2 * G::LBO) >> 4);
-              const uint32_t b_lo = b_lo0 + (uint32_t)((kk * 2 * lboB) >> 4);
-              umma_bf16_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, (ch | tap | kk) != 0 ? 1u : 0u);
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_bf16_lohi(tacc, a_lo + (uint32_t)((kk * 2 * G::LBO) >> 4), a_hi,
+                                 b_lo + (uint32_t)((kk * 2 * lboB) >> 4), b_hi, idesc, kk == 0 ? accum : 1u);
+              }
+              accum = 1u;
+              a_lo += (uint32_t)(G::slot(0, dx + 1) - G::slot(0, dx));      // next tap of this row (compile time per dx
+              b_lo += (uint32_t)(stageB >> 4);                              //  only through the unrolled kk loop)
             }
-            if (!a.resident) umma_commit(&emptyB[rb.slot]);
+            a_lo += (uint32_t)(G::slot(1, 0) - G::slot(0, KS));
           }
-          if (!a.resident) rb.advance();
+          b_res = b_lo;
           PROF_ADD(8, tp);
+        } else {
+#pragma unroll 1
+          for (int dy = 0; dy < KS; ++dy) {
+#pragma unroll 1
+            for (int dx = 0; dx < KS; ++dx) {
+              tp = PROF_T();
+              mbar_wait(&fullB[rb.slot], rb.phase, 105);
+              tc_fence_after();
+              PROF_ADD(7, tp);
+              tp = PROF_T();
+              const uint32_t b_lo = umma_desc_lo(b0 + rb.slot * stageB, lboB);
+              if (leader) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_bf16_lohi(tacc, a_lo + (uint32_t)((kk * 2 * G::LBO) >> 4), a_hi,
+                                 b_lo + (uint32_t)((kk * 2 * lboB) >> 4), b_hi, idesc, kk == 0 ? accum : 1u);
+                umma_commit(&emptyB[rb.slot]);
+              }
+              accum = 1u;
+              rb.advance();
+              a_lo += (uint32_t)(G::slot(0, dx + 1) - G::slot(0, dx));
+              PROF_ADD(8, tp);
+            }
+            a_lo += (uint32_t)(G::slot(1, 0) - G::slot(0, KS));
+          }
         }
         if (leader) umma_commit(&emptyA[ra.slot]);
         ra.advance();
-        b_res += (uint32_t)((ntaps * stageB) >> 4);
       }
       if (leader) umma_commit(&tmem_full[ab]);
       __syncwarp();
