@@ -630,33 +630,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         return mask;
       };
 
-      // Software pipeline: the loads of stage s+1 are in flight while stage s is transformed and stored.
+      // Software pipeline over NB register buffers used round-robin (the loop body is unrolled NB times so every
+      // buffer index is static): while stage s is transformed and stored, the loads of stages s+1 .. s+NB-1 are
+      // in flight -- two further stages for the 1x1 layers, whose 16 KB stages would otherwise expose the HBM
+      // latency once per stage.
+      constexpr int NB = KS == 1 ? 3 : 2;
       int ch = 0;
-      bool have = it.valid();
-      uint4 qn[BATCH];
-      uint32_t mask_n = 0;
-      Src cur;
-      if (have) {
-        cur = describe(it, ch);
-        mask_n = issue(cur, qn);
-      }
-      while (have) {
-        uint4 qc[BATCH];
-#pragma unroll
-        for (int i = 0; i < BATCH; ++i) qc[i] = qn[i];
-        const uint32_t mask_c = mask_n;
-        const int key_c = cur.key;
-        // advance to the next stage and put its loads in flight
-        if (++ch == nchunks) { ch = 0; it.next(); }
-        have = it.valid();
+      bool more = it.valid();
+      uint4 q[NB][BATCH];
+      uint32_t mk[NB];
+      int key[NB];
+      bool has[NB];
+      auto fetch = [&](uint4* qq, uint32_t& m, int& k) -> bool {      // puts the next stage's loads in flight
+        if (!more) return false;
         long long tp = PROF_T();
-        if (have) {
-          cur = describe(it, ch);
-          mask_n = issue(cur, qn);
-        }
+        const Src sd = describe(it, ch);
+        m = issue(sd, qq);
+        k = sd.key;
+        if (++ch == nchunks) { ch = 0; it.next(); }
+        more = it.valid();
         PROF_ADD(3, tp);
+        return true;
+      };
+      auto consume = [&](const uint4* qq, uint32_t mask_c, int key_c) {
         load_affine(key_c);
-        tp = PROF_T();
+        long long tp = PROF_T();
         if (!first_lap) mbar_wait(&emptyA[ra.slot], ra.phase ^ 1, 101);
         PROF_ADD(2, tp);
         tp = PROF_T();
@@ -667,13 +665,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         for (int i = 0; i < BATCH; ++i) {
           const bool on = (SWEEP * (i + 1) <= G::NSLOT) || ((act_mask >> i) & 1u);
           if (on) {
-            uint4 o = transform(qc[i]);
+            uint4 o = transform(qq[i]);
             if (!((mask_c >> i) & 1u)) o = make_uint4(0u, 0u, 0u, 0u);
             *reinterpret_cast<uint4*>(stage + soff[i]) = o;
           }
         }
         publish();
         PROF_ADD(4, tp);
+      };
+#pragma unroll
+      for (int j = 0; j < NB; ++j) has[j] = fetch(q[j], mk[j], key[j]);
+      while (has[0]) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          if (!has[j]) break;
+          consume(q[j], mk[j], key[j]);
+          has[j] = fetch(q[j], mk[j], key[j]);
+        }
       }
     } else {
       for (; it.valid(); it.next()) {

@@ -127,30 +127,46 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ parti
 }
 
 // ---- GroupNorm finalize: partial sums -> per-(image,channel) affine (with time modulation) -------
-// grid = B, block = 32*G threads (one warp per group reduces the tiles in a fixed order).
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, int ntile, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, const float* __restrict__ t_scale,
-                                   const float* __restrict__ t_shift, int t_ld, float* __restrict__ scale_out,
-                                   float* __restrict__ shift_out, int C, int G, float inv_count, float eps) {
-  __shared__ float stat[64][2];
-  const int b = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float s1 = 0.f, s2 = 0.f;
-  for (int t = lane; t < ntile; t += 32) {
-    const float* src = partial + (((size_t)b * ntile + t) * G + g) * 2;
-    s1 += src[0];
-    s2 += src[1];
+// grid = B, block = 512 threads.  The partial sums of image b are a [ntile][2G] matrix: thread t owns column
+// t % 2G and the rows t / 2G, t / 2G + 512 / 2G, ... (coalesced 8G-byte rows, four independent accumulators),
+// then the row lanes are folded through shared memory in a fixed order (deterministic, sharding-invariant).
+constexpr int kGnFinThreads = 512;
+__global__ void __launch_bounds__(kGnFinThreads)
+gn_finalize_kernel(const float* __restrict__ partial, int ntile, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const float* __restrict__ t_scale,
+                   const float* __restrict__ t_shift, int t_ld, float* __restrict__ scale_out,
+                   float* __restrict__ shift_out, int C, int G, float inv_count, float eps) {
+  __shared__ float red[kGnFinThreads];
+  __shared__ float stat[32][2];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int ncol = 2 * G, col = tid % ncol, rl = tid / ncol, nrl = kGnFinThreads / ncol;
+  const float* src = partial + (size_t)b * ntile * ncol + col;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rl < nrl) {
+    int t = rl;
+    for (; t + 3 * nrl < ntile; t += 4 * nrl) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += src[(size_t)(t + u * nrl) * ncol];
+    }
+    for (; t < ntile; t += nrl) acc[0] += src[(size_t)t * ncol];
   }
-  s1 = warp_sum(s1);
-  s2 = warp_sum(s2);
-  if (lane == 0) {
-    const float mean = s1 * inv_count;
-    const float var = fmaxf(s2 * inv_count - mean * mean, 0.f);
-    stat[g][0] = mean;
-    stat[g][1] = rsqrtf(var + eps);
+  red[tid] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncthreads();
+  if (tid < ncol) {
+    float sum = 0.f;
+    for (int r = 0; r < nrl; ++r) sum += red[r * ncol + tid];
+    red[tid] = sum;                                   // [g][sum, sum of squares]; rows >= 1 are dead by now
+  }
+  __syncthreads();
+  if (tid < G) {
+    const float mean = red[2 * tid] * inv_count;
+    const float var = fmaxf(red[2 * tid + 1] * inv_count - mean * mean, 0.f);
+    stat[tid][0] = mean;
+    stat[tid][1] = rsqrtf(var + eps);
   }
   __syncthreads();
   const int cpg = C / G;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int c = tid; c < C; c += kGnFinThreads) {
     const float mean = stat[c / cpg][0], rstd = stat[c / cpg][1];
     float sc = rstd * gamma[c];
     float sh = beta[c] - mean * sc;
@@ -305,9 +321,9 @@ int idiff_gn_finalize(const float* partial, int ntile, const float* gamma, const
   IDIFF_REQUIRE(partial && gamma && beta && scale_out && shift_out, "gn_finalize: null pointer");
   IDIFF_REQUIRE(B > 0 && ntile > 0 && G > 0 && G <= 32 && C % G == 0 && count_per_group > 0, "gn_finalize: bad sizes");
   IDIFF_REQUIRE((t_scale == nullptr) == (t_shift == nullptr), "gn_finalize: t_scale/t_shift must come together");
-  gn_finalize_kernel<<<B, 32 * G, 0, as_stream(stream)>>>(partial, ntile, gamma, beta, t_scale, t_shift, t_ld,
-                                                          scale_out, shift_out, C, G, 1.0f / (float)count_per_group,
-                                                          eps);
+  gn_finalize_kernel<<<B, kGnFinThreads, 0, as_stream(stream)>>>(partial, ntile, gamma, beta, t_scale, t_shift, t_ld,
+                                                                 scale_out, shift_out, C, G,
+                                                                 1.0f / (float)count_per_group, eps);
   return check_launch("gn_finalize");
 }
 
