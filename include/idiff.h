@@ -150,9 +150,17 @@ int idiff_conv_gemm_gn_rows(int H, int W);
  * bias, PLAIN epilogue, fp32 weights [N][k][k][cin]).  Used for validation of the tensor-core path. */
 int idiff_conv_ref(const idiff_gemm_params* p, const float* w_f32, float* out_f32, void* stream);
 
-/* Stem: cat([x - mu, mu]) -> 7x7 conv (pad 3) -> bf16 NHWC [B,H,W,N].  w: fp32 [N][7][7][2]. */
+/* Stem: cat([x - mu, mu]) -> 7x7 conv (pad 3) -> bf16 NHWC [B,H,W,N].  w: fp32 [N][7][7][2].
+ * CUDA-core fp32 version, kept as the validation reference of idiff_stem_conv7_tc. */
 int idiff_stem_conv7(const float* x, const float* mu, const float* w, const float* bias, void* out,
                      int B, int H, int W, int N, void* stream);
+
+/* Same layer on tcgen05 (the production path): in-kernel im2col of the fp32 patch into a bf16 hi/lo pair of A
+ * blocks (activations keep ~16 mantissa bits), weights + bias pre-packed on the host into the kernel's
+ * shared-memory image (instancediff_b200/packing.py::pack_stem_weight, idiff_stem_packed_bytes() bytes). N = 64. */
+int idiff_stem_conv7_tc(const float* x, const float* mu, const void* w_packed, void* out, int B, int H, int W,
+                        void* stream);
+int idiff_stem_packed_bytes(void);
 
 /* Head: 3x3 conv C -> 1 channel, fp32 out [B,1,H,W].  w: fp32 [3][3][C]. */
 int idiff_head_conv3(const void* src, const float* w, float bias, float* out, int B, int H, int W, int C,

@@ -56,6 +56,8 @@ SIGNATURES = {
     "idiff_conv_gemm_gn_rows": (C.c_int, [C.c_int, C.c_int]),
     "idiff_conv_ref": (C.c_int, [C.POINTER(GemmParams), c_ptr, c_ptr, c_ptr]),
     "idiff_stem_conv7": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr]),
+    "idiff_stem_conv7_tc": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr]),
+    "idiff_stem_packed_bytes": (C.c_int, []),
     "idiff_head_conv3": (C.c_int, [c_ptr, c_ptr, C.c_float, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr]),
     "idiff_time_embed": (C.c_int, [c_ptr, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                    C.c_int, C.c_int, C.c_int, c_ptr]),

@@ -51,16 +51,28 @@ IDIFF_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait (~1 s).  `code` identifies the call site in the watchdog word.  Waiting warps back off with
-// nanosleep so they do not steal issue slots from the working warps; the clock / watchdog word are read only
-// every 256 polls.
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase flips or ~`ns` elapse, so
+// a waiting role issues (almost) no instructions -- the SM is instruction-issue bound in the epilogue-heavy
+// layers and every polling instruction is taken from the working warps.
+IDIFF_DEVINL bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait (~1 s).  `code` identifies the call site in the watchdog word.  The clock / watchdog word are
+// read only every 64 (long, hardware-suspended) polls.
 IDIFF_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity, int code) {
   if (mbar_try_wait(bar, parity)) return;
   uint64_t t0 = 0;
   uint32_t polls = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(64);
-    if ((++polls & 255u) == 0) {
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if ((++polls & 63u) == 0) {
       if (*((volatile int*)&g_watchdog) != 0) return;
       const uint64_t now = globaltimer_ns();
       if (t0 == 0) t0 = now;

@@ -6,7 +6,7 @@
 namespace idiff {
 
 struct SmemPlan {
-  int SA, SB, resident, stageA, stageB, offA, offB, offP, offImg, offOut, offRes, nbuf_out, res_stride, total;
+  int SA, SB, resident, stageA, stageB, offA, offB, offP, offImg, offOut, offRes, nbuf_out, res_stride, res_nbuf, total;
 };
 
 static int stage_a_bytes(int ks) {
@@ -17,7 +17,7 @@ static bool tma_residuals(const idiff_gemm_params& p) { return p.NT == 64 && (p.
 // Layout: [header][output staging][residual staging][A stages][weights][column params][per-image params].
 // Weights stay RESIDENT for the whole (persistent) CTA when all of them fit next to at least two A stages;
 // otherwise they stream through a ring of SB stages.
-static SmemPlan plan_smem_n(const idiff_gemm_params& p, int nbuf_out) {
+static SmemPlan plan_smem_n(const idiff_gemm_params& p, int nbuf_out, int res_nbuf) {
   SmemPlan s;
   const int nchunks = (p.cin0 + p.cin1) / 64;
   const int nk = nchunks * p.ksize * p.ksize;
@@ -29,7 +29,8 @@ static SmemPlan plan_smem_n(const idiff_gemm_params& p, int nbuf_out) {
   const int ibytes = (p.bias_img || p.res0_scale) ? kImgBytes : 0;
   s.offOut = kHeader;
   s.offRes = s.offOut + kEpiWarps * s.nbuf_out * kStageTile;
-  s.offA = s.offRes + kEpiWarps * s.res_stride;
+  s.res_nbuf = s.res_stride ? res_nbuf : 1;
+  s.offA = s.offRes + kEpiWarps * s.res_nbuf * s.res_stride;
   const int budget = kSmemLimit - s.offA - pbytes - ibytes;
   const long wbytes = (long)nk * s.stageB * (p.N / p.NT);           // every N tile
   s.resident = (p.w_image_stride == 0 && wbytes + 2 * s.stageA <= budget) ? 1 : 0;
@@ -58,13 +59,20 @@ static SmemPlan plan_smem_n(const idiff_gemm_params& p, int nbuf_out) {
 
 // A second output staging tile per warp only pays when a row has several 64-channel boxes (NT > 64) and it
 // does not cost pipeline depth.
+static bool no_worse(const SmemPlan& s2, const SmemPlan& s1) {
+  return s2.total <= kSmemLimit && s2.resident == s1.resident && s2.SA >= (s1.SA < 3 ? s1.SA : 3) &&
+         (s2.resident || s2.SB >= (s1.SB < 4 ? s1.SB : 4));
+}
+// The same rule decides on a second set of residual staging tiles (TMA residuals of the NEXT item prefetched).
 static SmemPlan plan_smem(const idiff_gemm_params& p) {
-  const SmemPlan s1 = plan_smem_n(p, 1);
+  const SmemPlan s1 = plan_smem_n(p, 1, 1);
+  if (tma_residuals(p)) {
+    const SmemPlan s2 = plan_smem_n(p, 1, 2);
+    return no_worse(s2, s1) ? s2 : s1;
+  }
   if (p.NT == 64 || p.epi == IDIFF_EPI_GEGLU) return s1;
-  const SmemPlan s2 = plan_smem_n(p, 2);
-  const bool ok = s2.total <= kSmemLimit && s2.resident == s1.resident && s2.SA >= (s1.SA < 3 ? s1.SA : 3) &&
-                  (s2.resident || s2.SB >= (s1.SB < 4 ? s1.SB : 4));
-  return ok ? s2 : s1;
+  const SmemPlan s2 = plan_smem_n(p, 2, 1);
+  return no_worse(s2, s1) ? s2 : s1;
 }
 
 int watchdog_conv(int clear) {
@@ -182,7 +190,7 @@ int idiff_conv_gemm(const idiff_gemm_params* pp, void* stream) {
   a.p = *pp;
   const SmemPlan s = plan_smem(*pp);
   a.SA = s.SA; a.SB = s.SB; a.resident = s.resident; a.offA = s.offA; a.offB = s.offB; a.offP = s.offP;
-  a.offImg = s.offImg; a.offOut = s.offOut; a.offRes = s.offRes; a.nbuf_out = s.nbuf_out; a.res_stride = s.res_stride;
+  a.offImg = s.offImg; a.offOut = s.offOut; a.offRes = s.offRes; a.nbuf_out = s.nbuf_out; a.res_stride = s.res_stride; a.res_nbuf = s.res_nbuf;
   a.tiles_x = (pp->W + TILE_W - 1) / TILE_W;
   a.tiles_y = (pp->H + TILE_H - 1) / TILE_H;
   a.ntiles_n = pp->N / pp->NT;

@@ -67,7 +67,8 @@ struct KArgs {
   idiff_gemm_params p;
   int SA, SB, resident, offA, offB, offP, offImg, offOut, offRes;
   int nbuf_out;                       // staging tiles per epilogue warp for the output (1 or 2)
-  int res_stride;                     // bytes of residual staging per epilogue warp (4 KB per TMA residual)
+  int res_stride;                     // bytes of ONE residual staging set per epilogue warp (4 KB per TMA residual)
+  int res_nbuf;                       // residual staging sets per warp: 2 = the next item's tiles are prefetched
   int tiles_x, tiles_y, ntiles_n, total_items;
   unsigned long long* prof;           // 16 counters of CTA 0 (IDIFF_PROF builds), or nullptr
   alignas(64) CUtensorMap tm_out;     // [B][H][W][out cols] bf16, box {64, 8, 4, 1}, 128B swizzle
@@ -203,8 +204,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* tmem_full = emptyB + kMaxSB;           // [2]
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
   uint64_t* wres_bar = tmem_empty + 2;             // resident weights landed
-  uint64_t* res_bar = wres_bar + 1;                // [8] residual tile landed (per epilogue warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
+  uint64_t* res_bar = wres_bar + 1;                // [8][2] residual tiles landed (per epilogue warp and staging set)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef IDIFF_PROF
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     for (int i = 0; i < a.SB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps / 2); }
     mbar_init(wres_bar, 1);
-    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     mbar_fence_init();
   }
   if (warp == kWarpMma) tmem_alloc(tmem_slot, tmem_cols);
@@ -266,19 +267,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const bool img_params = p.bias_img != nullptr || p.res0_scale != nullptr;
     float* pimg = reinterpret_cast<float*>(smem + a.offImg) + grp * (3 * 256);   // [bias_img | res0_scale | res0_shift][256]
     uint8_t* ostage = smem + a.offOut + warp * (a.nbuf_out * kStageTile);
-    uint8_t* rstage = smem + a.offRes + warp * a.res_stride;                     // [res0 tile][res1 tile]
-    uint8_t* rstage1 = rstage + (p.res0 ? kStageTile : 0);
-    uint64_t* rbar = &res_bar[warp];
+    uint8_t* rstage_w = smem + a.offRes + warp * (a.res_nbuf * a.res_stride);    // [set][res0 tile | res1 tile]
+    const int res1_off = p.res0 ? kStageTile : 0;
+    uint64_t* rbar_w = &res_bar[2 * warp];
+    const bool res_tma = kTmaRes && (res0 || res1);
+    const bool res_pref = a.res_nbuf > 1;
+    // puts the residual tiles of item `ri` (this group's u-th item) in flight into staging set u & (nbuf-1)
+    auto issue_residuals = [&](const ItemIter& ri, int u) {
+      if (lane == 0) {
+        const int set = res_pref ? (u & 1) : 0;
+        uint8_t* dst = rstage_w + set * a.res_stride;
+        uint64_t* bar = rbar_w + set;
+        mbar_arrive_expect_tx(bar, (uint32_t)kStageTile * ((res0 ? 1u : 0u) + (res1 ? 1u : 0u)));
+        if (res0) tma_load_4d(dst, &a.tm_res0, ri.nt * NT, ri.ox0(), ri.oy0() + 4 * quarter, ri.b, bar);
+        if (res1) tma_load_4d(dst + res1_off, &a.tm_res1, ri.nt * NT, ri.ox0(), ri.oy0() + 4 * quarter, ri.b, bar);
+      }
+    };
     const uint32_t row_off = (uint32_t)lane * 128u, swz = (uint32_t)(lane & 7);
     const bool two_bufs = a.nbuf_out > 1;
     int obuf = 0;
     asm volatile("bar.sync 3, 256;" ::: "memory");                // pcache visible to both groups
 
     long long pacc9 = 0, pacc10 = 0;
-    int it_local = 0, mine = 0, img_key = -1;
+    int mine = 0, img_key = -1;
     ItemIter it;
-    for (it.init(a, blockIdx.x, gridDim.x); it.valid(); it.next(), ++it_local) {
-      if ((it_local & 1) != grp) continue;                        // the other group's accumulator buffer
+    it.init(a, blockIdx.x + grp * gridDim.x, 2 * gridDim.x);      // this group's items: every second one of the CTA
+    if (res_tma && res_pref && it.valid()) issue_residuals(it, 0);
+    for (; it.valid(); it.next()) {
       const int b = it.b, n0 = it.nt * NT;
       const int oy = it.oy0() + ti, ox = it.ox0() + tj;
       const bool valid = (oy < p.H) && (ox < p.W);
@@ -287,12 +302,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const int by = it.oy0() + 4 * quarter;                      // first tile row of this warp's TMA box
 
       // residual tiles by TMA, issued before the accumulator is ready
-      if (kTmaRes && (res0 || res1)) {
-        __syncwarp();                                             // every lane is done with the previous tile
-        if (lane == 0) {
-          mbar_arrive_expect_tx(rbar, (uint32_t)kStageTile * ((res0 ? 1u : 0u) + (res1 ? 1u : 0u)));
-          if (res0) tma_load_4d(rstage, &a.tm_res0, n0, it.ox0(), by, b, rbar);
-          if (res1) tma_load_4d(rstage1, &a.tm_res1, n0, it.ox0(), by, b, rbar);
+      const uint8_t* rstage = rstage_w + (res_pref ? (mine & 1) * a.res_stride : 0);
+      if (res_tma) {
+        __syncwarp();                                             // every lane is done with the tile being replaced
+        if (res_pref) {                                           // next item's tiles: a whole item of lead time
+          ItemIter nx = it;
+          nx.next();
+          if (nx.valid()) issue_residuals(nx, mine + 1);
+        } else {
+          issue_residuals(it, 0);
         }
       }
       float mean_in = 0.f, rstd_in = 1.f;
@@ -318,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
       // accumulator chunk -> value after LayerNorm fold + biases (32 columns starting at global column n)
       auto apply_base = [&](float* v, int n) {
-        if (p.row_stats) for_cols32(pcache + p.N + n, v, [&](float x, float c) { return (x - mean_in * c) * rstd_in; });
+        if (p.row_stats) for_cols32(pcache + p.N + n, v, [&](float x, float c) { return fmaf(-mean_in, c, x) * rstd_in; });
         if (p.bias) for_cols32(pcache + n, v, [](float x, float c) { return x + c; });
         if (p.bias_img) for_cols32(pimg + (n - n0), v, [](float x, float c) { return x + c; });
       };
@@ -327,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (!res0 && !res1) return;
         if (kTmaRes) {
           if (!res_waited) {
-            mbar_wait(rbar, (uint32_t)(mine & 1), 108);
+            mbar_wait(rbar_w + (res_pref ? (mine & 1) : 0), (uint32_t)((res_pref ? (mine >> 1) : mine) & 1), 108);
             res_waited = true;
           }
           const uint32_t cb = (uint32_t)((n - n0) >> 3);          // first 16 B chunk of these 32 columns
@@ -347,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             float rr[32];
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
-              unpack_bf16x8(*reinterpret_cast<const uint4*>(rstage1 + row_off + (((cb + q4) ^ swz) << 4)),
+              unpack_bf16x8(*reinterpret_cast<const uint4*>(rstage + res1_off + row_off + (((cb + q4) ^ swz) << 4)),
                             rr + q4 * 8);
 #pragma unroll
             for (int q = 0; q < 32; ++q) v[q] += rr[q];
@@ -475,13 +493,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
 
           if (EPI == IDIFF_EPI_QSOFTMAX && ncol0 < 128) {
-            float mx = v[0];
+            float m4[4] = {v[0], v[1], v[2], v[3]};       // four independent chains instead of one 32-long one
 #pragma unroll
-            for (int q = 1; q < 32; ++q) mx = fmaxf(mx, v[q]);
-            float sm = 0.f;
+            for (int q = 4; q < 32; ++q) m4[q & 3] = fmaxf(m4[q & 3], v[q]);
+            const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int q = 0; q < 32; ++q) { v[q] = __expf(v[q] - mx); sm += v[q]; }
-            const float inv = p.qscale / sm;
+            for (int q = 0; q < 32; ++q) { v[q] = __expf(v[q] - mx); s4[q & 3] += v[q]; }
+            const float inv = p.qscale / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
 #pragma unroll
             for (int q = 0; q < 32; ++q) v[q] *= inv;
             store32(v, cc);
@@ -512,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       if (grp == 0) PROF_ADD(10, tp);
     }
     if (kTmaOut && lane == 0) bulk_wait_all();              // staging tiles must outlive the last TMA store
-    if (prof && tid == 0) { a.prof[9] = pacc9; a.prof[10] = pacc10; a.prof[1] = it_local; }
+    if (prof && tid == 0) { a.prof[9] = pacc9; a.prof[10] = pacc10; a.prof[1] = mine; }
   } else if (warp < kWarpB) {
     // ============================== A producers ==============================================
     const int ltid = tid - kEpiThreads;

@@ -69,6 +69,18 @@ def stem_conv7(x, mu, w_nhwc, bias):
     return out
 
 
+def stem_conv7_tc(x, mu, w, bias):
+    """Production stem (tcgen05): w [64,2,7,7] fp32, bias [64] -> bf16 NHWC [B,H,W,64]."""
+    from .packing import pack_stem_weight
+    B, _, H, W = x.shape
+    wp = pack_stem_weight(w.float(), bias.float()).to(x.device)
+    assert wp.numel() * 2 == _lib.lib().idiff_stem_packed_bytes()
+    out = torch.empty(B, H, W, 64, dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().idiff_stem_conv7_tc(x.data_ptr(), mu.data_ptr(), wp.data_ptr(), out.data_ptr(), B, H, W, _s(x)),
+          "stem_conv7_tc")
+    return out
+
+
 def head_conv3(src, w_hwc, bias: float):
     B, H, W, Cc = src.shape
     out = torch.empty(B, 1, H, W, dtype=torch.float32, device=src.device)

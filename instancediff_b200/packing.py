@@ -56,3 +56,23 @@ def interleave_geglu(w: torch.Tensor, b: torch.Tensor):
     wi = torch.stack([w[:F], w[F:]], dim=1).reshape(2 * F, -1)
     bi = torch.stack([b[:F], b[F:]], dim=1).reshape(2 * F)
     return wi, bi
+
+
+def pack_stem_weight(w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """Stem 7x7 conv (w: [64, 2, 7, 7], bias: [64]) -> the shared-memory image idiff_stem_conv7_tc expects.
+
+    K index k' = tap*2 + ci (tap = ky*7 + kx) for k' < 98; k' = 98 / 99 hold the bias as a bf16 hi / lo pair (the
+    kernel's A rows carry the constant 1 there); zero padding up to 112.  The kernel stores its A block twice
+    (bf16 hi and lo parts of the fp32 activations), so the 112 weights are repeated for the second half, with
+    the bias rows cleared.  Layout: [28 K-groups][64 n][8 k] bf16 (LBO = 1024 B, SBO = 128 B).
+    """
+    N = w.shape[0]
+    assert tuple(w.shape) == (N, 2, 7, 7) and N == 64, w.shape
+    wk = torch.zeros(N, 112, dtype=torch.float32, device=w.device)
+    wk[:, :98] = w.permute(0, 2, 3, 1).reshape(N, 98)
+    lo_half = wk.clone()
+    b_hi = bias.to(torch.bfloat16).float()
+    wk[:, 98] = b_hi
+    wk[:, 99] = bias - b_hi
+    full = torch.cat([wk, lo_half], dim=1)                      # [N, 224]
+    return full.reshape(N, 28, 8).permute(1, 0, 2).contiguous().to(torch.bfloat16).reshape(-1)

@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 from ._lib import EPI_GEGLU, EPI_LN_OUT, EPI_PLAIN, EPI_QSOFTMAX, GemmParams, check
-from .packing import fold_layernorm, interleave_geglu, pack_conv_weight
+from .packing import fold_layernorm, interleave_geglu, pack_conv_weight, pack_stem_weight
 
 GN_GROUPS = 8
 TILE_H, TILE_W = 16, 8
@@ -238,7 +238,7 @@ class ConditionalUNet:
                 conv_entry(f + ".proj_out")
 
         # stem / head / time
-        pk["init_conv"] = dict(w=f32(P["init_conv.weight"].permute(0, 2, 3, 1)), bias=f32(P["init_conv.bias"]))
+        pk["init_conv"] = dict(w=pack_stem_weight(f32(P["init_conv.weight"]), f32(P["init_conv.bias"])).to(self.device))
         pk["final_conv"] = dict(w=f32(P["final_conv.weight"][0].permute(1, 2, 0)),
                                 bias=float(P["final_conv.bias"].reshape(-1)[0].item()))
         self._res_names: List[str] = []
@@ -576,7 +576,7 @@ class _Plan:
 
         x_first = self.act(H, W, nf)
         self.named["init_conv"] = x_first
-        self._stem_tail = (_ptr(pk["init_conv"]["w"]), _ptr(pk["init_conv"]["bias"]), _ptr(x_first.t), B, H, W, nf)
+        self._stem_tail = (_ptr(pk["init_conv"]["w"]), _ptr(x_first.t), B, H, W)
         self.n_launch += 1
 
         h = x_first
@@ -618,7 +618,7 @@ class _Plan:
         s = stream.cuda_stream
         calls = [("time_embed", "", 0.0, lambda: check(L.idiff_time_embed(None, t_scalar, *self._time_args, s))),
                  ("stem_conv7", f"@{self.H}x{self.W}", 2.0 * self.B * self.H * self.W * 98 * self.net.nf,
-                  lambda: check(L.idiff_stem_conv7(xt.data_ptr(), cond.data_ptr(), *self._stem_tail, s)))]
+                  lambda: check(L.idiff_stem_conv7_tc(xt.data_ptr(), cond.data_ptr(), *self._stem_tail, s)))]
         for op, (kind, flops, label) in zip(self.ops, self.op_info):
             calls.append((kind, label, flops, (lambda op=op: op(s))))
         acc = [0.0] * len(calls)
@@ -640,6 +640,6 @@ class _Plan:
         s = torch.cuda.current_stream(self.dev).cuda_stream
         t_ptr = t_dev if (t_dev is None or isinstance(t_dev, int)) else t_dev.data_ptr()
         check(L.idiff_time_embed(t_ptr, t_scalar, *self._time_args, s), "time_embed")
-        check(L.idiff_stem_conv7(xt.data_ptr(), cond.data_ptr(), *self._stem_tail, s), "stem_conv7")
+        check(L.idiff_stem_conv7_tc(xt.data_ptr(), cond.data_ptr(), *self._stem_tail, s), "stem_conv7")
         for op in self.ops:
             op(s)

@@ -32,6 +32,26 @@ def test_stem_conv7():
     assert rel_err(out, ref) <= 5e-3, describe(out, ref, "stem")
 
 
+@pytest.mark.parametrize("shape", [(2, 40, 24), (1, 16, 8), (3, 64, 64), (1, 21, 13)])
+def test_stem_conv7_tensor_core(shape):
+    """tcgen05 stem (in-kernel im2col, bf16 hi/lo activations, bf16 weights, bias folded into the GEMM) vs the fp32
+    convolution; ragged and single-tile shapes included.  Tolerance = bf16 rounding of weights and output."""
+    from instancediff_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    B, H, W = shape
+    x, mu = torch.randn(B, 1, H, W, generator=g).cuda(), torch.randn(B, 1, H, W, generator=g).cuda()
+    w = ((torch.rand(64, 2, 7, 7, generator=g) * 2 - 1) / 10).cuda()
+    b = (torch.rand(64, generator=g) - 0.5).cuda()
+    out = ops.stem_conv7_tc(x, mu, w, b)
+    ref = F.conv2d(torch.cat([x - mu, mu], 1), w, b, padding=3).permute(0, 2, 3, 1)
+    assert rel_err(out, ref) <= 5e-3, describe(out, ref, "stem tc")
+    # against the same bf16-rounded weights the error is the output rounding only (activations are hi+lo exact)
+    ref_q = F.conv2d(torch.cat([x - mu, mu], 1), w.to(torch.bfloat16).float(), b, padding=3).permute(0, 2, 3, 1)
+    assert rel_err(out, ref_q) <= 4e-3, describe(out, ref_q, "stem tc vs bf16 weights")   # bf16 half-ulp = 2^-8
+    simt = ops.stem_conv7(x, mu, w.permute(0, 2, 3, 1).contiguous(), b)
+    assert rel_err(out, simt) <= 5e-3
+
+
 def test_head_conv3():
     from instancediff_b200 import ops
     g = torch.Generator().manual_seed(1)
