@@ -186,7 +186,9 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
 // layout/descriptor roles the self-attention V operand uses).  The Gram matrix over all 4 heads is computed at
 // once (M = 128) and only the 4 diagonal 32x32 blocks are kept.
 // =====================================================================================================
-constexpr int LA_CHUNK = 4096;                               // pixels per CTA
+// pixels per CTA: small enough that every level fills the GPU (a CTA walks its chunk serially; with 4096-pixel
+// chunks the 64x64 level ran on 32 CTAs and every level cost ~0.2 ms of latency regardless of its size)
+__host__ __device__ inline int la_chunk(int HW) { return HW >= 65536 ? 2048 : HW >= 16384 ? 1024 : 512; }
 constexpr int LA_SUB = 128;                                  // pixels per MMA batch (8 x K16)
 constexpr int LA_PLANE = LA_SUB * 16 + 32;                   // bytes between 8-channel planes
 constexpr int LA_OFF_E = 0;                                  // [16 planes] E tile  (A, MN-major: k-channels x pixels)
@@ -203,7 +205,7 @@ linattn_kmax_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ p
   __shared__ float red[16][128];
   const int tid = threadIdx.x, chunk = blockIdx.x, b = blockIdx.y, nchunk = gridDim.x;
   const int c8 = tid & 15, rg = tid >> 4;
-  const int r0 = chunk * LA_CHUNK, r1 = min(HW, r0 + LA_CHUNK);
+  const int r0 = chunk * la_chunk(HW), r1 = min(HW, r0 + la_chunk(HW));
   const __nv_bfloat16* kb = qkv + (size_t)b * HW * 384 + 128 + c8 * 8;
   float mx[8];
 #pragma unroll
@@ -270,7 +272,7 @@ linattn_gram_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
   for (int e = 0; e < 8; ++e) mloc[e] = kmax[c8 * 8 + e];
   const __nv_bfloat16* kb = qkv + (size_t)b * HW * 384 + 128 + c8 * 8;
   const __nv_bfloat16* vb = kb + 128;
-  const int r_begin = chunk * LA_CHUNK, r_end = min(HW, r_begin + LA_CHUNK);
+  const int r_begin = chunk * la_chunk(HW), r_end = min(HW, r_begin + la_chunk(HW));
   int it = 0;
   for (int r0 = r_begin; r0 < r_end; r0 += LA_SUB, ++it) {
     uint4 qk[8], qv[8];
@@ -385,7 +387,7 @@ int idiff_set_debug_flags(int flags) {
 }
 
 size_t idiff_linattn_scratch_floats(int B, int HW) {
-  const size_t nchunk = (size_t)(HW + LA_CHUNK - 1) / LA_CHUNK;
+  const size_t nchunk = (size_t)(HW + la_chunk(HW) - 1) / la_chunk(HW);
   return (size_t)B * nchunk * (LA_PART + 128);               // Gram partials + per-chunk channel maxima
 }
 
@@ -394,7 +396,7 @@ int idiff_linattn_context(const void* qkv, const float* w_out, void* weff_packed
   IDIFF_REQUIRE(qkv && w_out && weff_packed && scratch && B > 0 && HW > 0, "linattn_context: bad arguments");
   IDIFF_REQUIRE(C == 64 || C == 128 || C == 256, "linattn_context: C must be 64/128/256");
   IDIFF_REQUIRE(aligned16(qkv), "linattn_context: 16 B alignment");
-  const int nchunk = (HW + LA_CHUNK - 1) / LA_CHUNK;
+  const int nchunk = (HW + la_chunk(HW) - 1) / la_chunk(HW);
   float* part = scratch;
   float* pmax = scratch + (size_t)B * nchunk * LA_PART;
   static bool attr = false;

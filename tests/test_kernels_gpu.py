@@ -49,7 +49,7 @@ def test_stem_conv7_tensor_core(shape):
     ref_q = F.conv2d(torch.cat([x - mu, mu], 1), w.to(torch.bfloat16).float(), b, padding=3).permute(0, 2, 3, 1)
     assert rel_err(out, ref_q) <= 4e-3, describe(out, ref_q, "stem tc vs bf16 weights")   # bf16 half-ulp = 2^-8
     simt = ops.stem_conv7(x, mu, w.permute(0, 2, 3, 1).contiguous(), b)
-    assert rel_err(out, simt) <= 5e-3
+    assert rel_err(out, simt) <= 8e-3          # two bf16-rounded results may differ by one ulp (2^-7)
 
 
 def test_head_conv3():
