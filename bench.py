@@ -239,11 +239,18 @@ def run_cuda(args):
     plan = net._plan(B, RES, RES, True)
     rows = plan.run_timed(xT, mu_d, 50.0, reps=3)
     by_kind = {}
-    for kind, label, flops, ms in rows:
+    split = {"kxk": dict(ms=0.0, flops=0.0, bytes=0.0, n=0), "1x1": dict(ms=0.0, flops=0.0, bytes=0.0, n=0)}
+    for kind, label, flops, ms, nbytes in rows:
         k = by_kind.setdefault(kind, dict(ms=0.0, flops=0.0, n=0))
         k["ms"] += ms
         k["flops"] += flops
         k["n"] += 1
+        if kind == "conv_gemm":                              # 3x3 / 4x4 convolutions vs 1x1 (linear) layers
+            c = split["1x1" if label.startswith("k1") else "kxk"]
+            c["ms"] += ms
+            c["flops"] += flops
+            c["bytes"] += nbytes
+            c["n"] += 1
     fwd_ms = sum(k["ms"] for k in by_kind.values())
     conv = by_kind["conv_gemm"]
     conv_tflops = conv["flops"] / (conv["ms"] / 1e3) / 1e12
@@ -292,6 +299,20 @@ def run_cuda(args):
                      "share_of_forward": conv["ms"] / fwd_ms,
                      "note": "achieved = sum of algorithmic 2*M*N*K over the conv_gemm launches of one forward / sum of their "
                              "CUDA-event durations; peak = MEASURED_PEAKS bf16 sustained (kernel timed inside a long step)"},
+        # the same launches split by what bounds them (tensor roofline for the convolutions,
+        # HBM roofline for the 1x1 / linear layers, whose arithmetic intensity is below the ridge)
+        "roofline_conv_kxk": {"bound": "tensor", "kernel": "conv_gemm_kernel, 3x3 and 4x4/s2 convolutions",
+                              "achieved": split["kxk"]["flops"] / (split["kxk"]["ms"] / 1e3) / 1e12, "peak": pk["tf_sustained"],
+                              "unit": "TFLOP/s",
+                              "frac": split["kxk"]["flops"] / (split["kxk"]["ms"] / 1e3) / 1e12 / pk["tf_sustained"],
+                              "launches_per_forward": split["kxk"]["n"], "ms_per_forward": split["kxk"]["ms"],
+                              "note": "Cout = 64 layers are capped at 64 cycles per M128xN64xK16 tcgen05.mma (shared-memory "
+                                      "operand reads), i.e. at half the tensor peak; see DESIGN.md section 4"},
+        "roofline_linear_1x1": {"bound": "hbm", "kernel": "conv_gemm_kernel, 1x1 / linear layers",
+                                "achieved": split["1x1"]["bytes"] / (split["1x1"]["ms"] / 1e3) / 1e9, "peak": pk["hbm"],
+                                "unit": "GB/s", "frac": split["1x1"]["bytes"] / (split["1x1"]["ms"] / 1e3) / 1e9 / pk["hbm"],
+                                "tflops": split["1x1"]["flops"] / (split["1x1"]["ms"] / 1e3) / 1e12,
+                                "launches_per_forward": split["1x1"]["n"], "ms_per_forward": split["1x1"]["ms"]},
         "roofline_sde": {"bound": "hbm", "kernel": "sde_step_kernel", "achieved": sde_gbs, "peak": pk["hbm"], "unit": "GB/s",
                          "frac": sde_gbs / pk["hbm"], "us_per_launch": sde_us, "bytes_per_element": 16},
         "forward_breakdown_ms": {k: round(v["ms"], 4) for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1]["ms"])},
@@ -305,9 +326,10 @@ def run_cuda(args):
                                           f"{dt:.1f} s of CPU work, extrapolated to T={T_STEPS}"}
     if args.dump_kernels and rank == 0:
         with open(args.dump_kernels, "w") as f:
-            f.write("kind,label,gflop,ms,tflops\n")
-            for kind, label, flops, ms in rows:
-                f.write(f"{kind},{label},{flops / 1e9:.3f},{ms:.4f},{(flops / (ms / 1e3) / 1e12) if ms > 0 else 0:.2f}\n")
+            f.write("kind,label,gflop,ms,tflops,algo_mbytes,algo_gbs\n")
+            for kind, label, flops, ms, nbytes in rows:
+                f.write(f"{kind},{label},{flops / 1e9:.3f},{ms:.4f},{(flops / (ms / 1e3) / 1e12) if ms > 0 else 0:.2f},"
+                        f"{nbytes / 1e6:.1f},{(nbytes / (ms / 1e3) / 1e9) if ms > 0 else 0:.0f}\n")
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

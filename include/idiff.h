@@ -204,6 +204,18 @@ int idiff_linattn_context(const void* qkv, const float* w_out /*[C][128]*/, void
                           float* scratch, int B, int HW, int C, void* stream);
 size_t idiff_linattn_scratch_floats(int B, int HW);
 
+/* Fused linear attention block for C = 64 / 128 (q, k, v never touch HBM; three passes over x):
+ *   out = x + LN_c(W_out (ctx^T q) + bias_out) * gain_out,  q = softmax_d(Wq x^) * qscale,
+ *   ctx[h] = softmax_n(Wk x^)[h] (Wv x^)[h]^T / HW,  x^ = (x - mean) * rstd from row_stats [B*HW][2].
+ * wq_packed / wk_packed: [128][C] weights with the pre-norm gain folded in, packed by pack_conv_weight(NT=128);
+ * wv: fp32 [128][C] (gain folded); w_out: fp32 [C][128]; weff_scratch: bf16 [B][C*128]; scratch:
+ * idiff_linattn_fused_scratch_floats(B, HW, C) floats.  HW must be a multiple of 128. */
+int idiff_linattn_fused(const void* x, const float* row_stats, const void* wq_packed, const void* wk_packed,
+                        const float* wv, const float* w_out, const float* bias_out, const float* gain_out,
+                        void* weff_scratch, void* out, float* scratch, int B, int HW, int C, float qscale, float ln_eps,
+                        void* stream);
+size_t idiff_linattn_fused_scratch_floats(int B, int HW, int C);
+
 /* Multi-head self-attention, head dim 32: qkv bf16 [B][L][3*C] (q|k|v, heads contiguous), out bf16
  * [B][L][C].  tcgen05 QK^T and PV with fp32 softmax. */
 int idiff_self_attention(const void* qkv, void* out, int B, int L, int heads, float scale, void* stream);

@@ -71,6 +71,9 @@ SIGNATURES = {
     "idiff_chan_ln": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_float, C.c_size_t, C.c_int, c_ptr]),
     "idiff_linattn_context": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr]),
     "idiff_linattn_scratch_floats": (C.c_size_t, [C.c_int, C.c_int]),
+    "idiff_linattn_fused": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                      C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, c_ptr]),
+    "idiff_linattn_fused_scratch_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "idiff_self_attention": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr]),
     "idiff_cross_vec": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr]),
     "idiff_f32_to_bf16": (C.c_int, [c_ptr, c_ptr, C.c_size_t, c_ptr]),

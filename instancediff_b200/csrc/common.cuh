@@ -51,6 +51,9 @@ IDIFF_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifndef IDIFF_MBAR_HINT_NS
+#define IDIFF_MBAR_HINT_NS 20000u
+#endif
 // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase flips or ~`ns` elapse, so
 // a waiting role issues (almost) no instructions -- the SM is instruction-issue bound in the epilogue-heavy
 // layers and every polling instruction is taken from the working warps.
@@ -71,7 +74,7 @@ IDIFF_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity, int code) {
   if (mbar_try_wait(bar, parity)) return;
   uint64_t t0 = 0;
   uint32_t polls = 0;
-  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+  while (!mbar_try_wait_hint(bar, parity, IDIFF_MBAR_HINT_NS)) {
     if ((++polls & 63u) == 0) {
       if (*((volatile int*)&g_watchdog) != 0) return;
       const uint64_t now = globaltimer_ns();

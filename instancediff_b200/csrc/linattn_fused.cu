@@ -1,0 +1,581 @@
+// Fused linear attention (UNet levels with C = 64 / 128 channels; SURVEY.md App. A `LinearAttention` under
+// Residual(PreNorm)):   y = x + LN_out( W_out * (ctx^T q) + b ),   q = softmax_d(Wq x^) * scale,
+//                       ctx[h] = softmax_n(Wk x^)[h] (Wv x^)[h]^T / HW,   x^ = ChanLayerNorm(x).
+//
+// The unfused chain (qkv GEMM -> k max -> context Gram -> merge -> output GEMM) moved 2176 B per pixel through HBM
+// (the 384-channel qkv tensor is written once and read twice).  Here q, k and v never exist in HBM: three passes
+// read x (128-256 B per pixel each) and only the result is written -- 4.2x less traffic at C = 64.
+//   pass 0  la_kmax : k^T = Wk x^^T per 128-pixel tile (tcgen05, M = 128 k-channels, N = 128 pixels): with the GEMM
+//                     transposed, a thread owns ONE k channel and the pixel maximum is a thread-local reduction.
+//   pass 1  la_ctx  : the same GEMM, e = exp(k - max) re-staged as a K-major A operand (K = pixels), then
+//                     S += e [x^ | 1]  (N = C + 16, x^ tile re-used as an MN-major B operand, accumulated in TMEM over
+//                     the CTA's whole chunk).  v is never formed:  ctx = (S Wv^T) / (rowsum HW)  is finished on
+//                     fp32 partial sums by la_merge, which also folds ctx into the per-image output weight
+//                     Weff[b] = W_out blockdiag(ctx^T).
+//   pass 2  la_out  : q = Wq x^ (N = 128), per-head softmax in registers, q re-staged as the A operand of
+//                     out = q Weff[b]^T (N = C), then bias, channel LayerNorm, gain, + x, bf16 store.
+// x^ = (x - mean) * rstd is formed by the tile loader from the producer's per-pixel LayerNorm statistics (the gain
+// is folded into the weights), so all three passes see bit-identical operands (exp(k - max) <= 1 exactly).
+// Serves `self.model(x, self.mu, t*scale, **kwargs)`, utils/sde_utils.py:198.
+#include "common.cuh"
+#include "host_common.h"
+
+namespace idiff {
+
+constexpr int LF_PX = 128;                      // pixels per tile
+constexpr int LF_XP = LF_PX * 16 + 16;          // x^ plane pitch: odd multiple of 16 B -> conflict-free loader stores
+constexpr int LF_WP = 128 * 16;                 // weight plane (128 rows x 8 channels), verbatim packed image
+constexpr int LF_TP = 128 * 16;                 // E / Q staging plane (128 rows x 16 B)
+constexpr float LF_LOG2E = 1.4426950408889634f;
+
+int watchdog_lattn(int clear) { return watchdog_read_tu(clear); }
+
+__host__ __device__ inline int lf_chunk(int HW) { return HW >= 65536 ? 2048 : HW >= 16384 ? 1024 : 512; }
+
+IDIFF_DEVINL float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ---- x^ tile loader: 128 pixels x C channels -> [C/8 planes][128 px][8 ch], normalised on the way ------------
+template <int C>
+struct XTile {
+  static constexpr int TPP = C / 8;              // threads (16 B vectors) per pixel
+  static constexpr int PPS = 256 / TPP;          // pixels per sweep of the 256 threads
+  static constexpr int NV = LF_PX / PPS;         // vectors per thread
+  uint4 q[NV];
+  float2 st[NV];
+  IDIFF_DEVINL void fetch(const __nv_bfloat16* __restrict__ xb, const float2* __restrict__ sb, int r0, int tid) {
+    const int c8 = tid % TPP, p0 = tid / TPP;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int r = r0 + p0 + PPS * i;
+      q[i] = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)r * C + c8 * 8));
+      st[i] = __ldg(sb + r);
+    }
+  }
+  IDIFF_DEVINL void store(uint8_t* sX, int tid) const {
+    const int c8 = tid % TPP, p0 = tid / TPP;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float f[8];
+      unpack_bf16x8(q[i], f);
+      const float a = st[i].y, bm = -st[i].x * st[i].y;         // (x - mean) * rstd
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], a, bm);
+      *reinterpret_cast<uint4*>(sX + c8 * LF_XP + (p0 + PPS * i) * 16) = pack_bf16x8(f);
+    }
+  }
+};
+
+IDIFF_DEVINL void copy_g2s(uint8_t* dst, const void* src, int bytes, int tid) {
+  for (int i = tid; i < bytes / 16; i += 256) reinterpret_cast<uint4*>(dst)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+}
+
+// D[tmem] (+)= A * B for one 128-wide tile: K = 16 * nk, both operand descriptors advance by fixed steps
+IDIFF_DEVINL void issue_mmas(uint32_t tacc, uint32_t a_lo, uint32_t a_hi, uint32_t a_step, uint32_t b_lo, uint32_t b_hi,
+                             uint32_t b_step, uint32_t idesc, int nk, uint32_t accum_first) {
+  for (int kk = 0; kk < nk; ++kk)
+    umma_bf16_lohi(tacc, a_lo + kk * a_step, a_hi, b_lo + kk * b_step, b_hi, idesc, kk == 0 ? accum_first : 1u);
+}
+
+// =====================================================================================================
+// pass 0: per-(image, chunk) maxima of k over the chunk's pixels.  grid = (nchunk, B), block = 256.
+// =====================================================================================================
+template <int C>
+struct KmaxSmem {
+  static constexpr int X = 0, W = X + (C / 8) * LF_XP, RED = W + (C / 8) * LF_WP, BAR = RED + 128 * 4, TOTAL = BAR + 32;
+};
+
+template <int C>
+__global__ void __launch_bounds__(256, C == 64 ? 2 : 1)
+la_kmax_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats, const void* __restrict__ wk,
+               float* __restrict__ pmax, int HW) {
+  using S = KmaxSmem<C>;
+  extern __shared__ __align__(128) uint8_t sm[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + S::BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  float* red = reinterpret_cast<float*>(sm + S::RED);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x, b = blockIdx.y, nchunk = gridDim.x;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  copy_g2s(sm + S::W, wk, (C / 8) * LF_WP, tid);
+  const __nv_bfloat16* xb = x + (size_t)b * HW * C;
+  const float2* sb = stats + (size_t)b * HW;
+  const int r_begin = chunk * lf_chunk(HW), r_end = min(HW, r_begin + lf_chunk(HW));
+  XTile<C> xt;
+  xt.fetch(xb, sb, r_begin, tid);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const bool leader = (warp == 0) && elect_one();
+  const uint32_t smem0 = smem_u32(sm);
+  const uint32_t idesc = umma_idesc_bf16(128, 128, 0);
+  const uint32_t w_lo = umma_desc_lo(smem0 + S::W, LF_WP), x_lo = umma_desc_lo(smem0 + S::X, LF_XP);
+  const uint32_t k_hi = umma_desc_hi(128);
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+
+  float mx = -INFINITY;
+  int it = 0;
+  for (int r0 = r_begin; r0 < r_end; r0 += LF_PX, ++it) {
+    xt.store(sm + S::X, tid);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (leader) {
+        issue_mmas(tmem, w_lo, k_hi, (2 * LF_WP) >> 4, x_lo, k_hi, (2 * LF_XP) >> 4, idesc, C / 16, 0u);
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    if (r0 + LF_PX < r_end) xt.fetch(xb, sb, r0 + LF_PX, tid);    // next tile's loads fly during the MMA + epilogue
+    mbar_wait(bar, it & 1, 401);
+    tc_fence_after();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float v[32];
+      tmem_ld32(lane_addr + j * 32, v);
+      float m4[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+      for (int qq = 4; qq < 32; ++qq) m4[qq & 3] = fmaxf(m4[qq & 3], v[qq]);
+      mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+    }
+    tc_fence_before();            // the barrier at the top of the next tile orders these reads before its MMA
+  }
+  // the two column halves of a row live in warps w and w + 4
+  __syncthreads();
+  if (warp >= 4) red[(warp & 3) * 32 + lane] = mx;
+  __syncthreads();
+  if (warp < 4) pmax[((size_t)b * nchunk + chunk) * 128 + warp * 32 + lane] = fmaxf(mx, red[warp * 32 + lane]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+// =====================================================================================================
+// pass 1: S[d][c] = sum_n exp(k[d,n] - max[d]) x^[n,c], rowsum[d] = sum_n exp(..).  grid = (nchunk, B), block = 256.
+// part: [B][nchunk][128][C + 1] fp32 (column C = rowsum).
+// =====================================================================================================
+template <int C>
+struct CtxSmem {
+  static constexpr int NP = C / 8 + 2;           // x^ planes + the constant [1 | 0] planes
+  static constexpr int X = 0, W = X + NP * LF_XP, E = W + (C / 8) * LF_WP, MAXV = E + 16 * LF_TP,
+                       BAR = MAXV + 128 * 4, TOTAL = BAR + 32;
+  static constexpr int TMEM_COLS = C == 64 ? 256 : 512;   // 128 (k tile) + C + 16 (S | rowsum), 32-column reads
+};
+
+template <int C>
+__global__ void __launch_bounds__(256, C == 64 ? 2 : 1)
+la_ctx_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats, const void* __restrict__ wk,
+              const float* __restrict__ pmax, float* __restrict__ part, int HW) {
+  using S = CtxSmem<C>;
+  extern __shared__ __align__(128) uint8_t sm[];
+  uint64_t* bar1 = reinterpret_cast<uint64_t*>(sm + S::BAR);
+  uint64_t* bar2 = bar1 + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar1 + 2);
+  float* kmax = reinterpret_cast<float*>(sm + S::MAXV);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x, b = blockIdx.y, nchunk = gridDim.x;
+  if (tid == 0) {
+    mbar_init(bar1, 1);
+    mbar_init(bar2, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, S::TMEM_COLS);
+  copy_g2s(sm + S::W, wk, (C / 8) * LF_WP, tid);
+  if (tid < 128) {                                            // exact channel maximum over the whole image
+    float m = -INFINITY;
+    for (int c = 0; c < nchunk; ++c) m = fmaxf(m, pmax[((size_t)b * nchunk + c) * 128 + tid]);
+    kmax[tid] = m * LF_LOG2E;
+  }
+  {                                                           // constant planes: ones (rowsum column), zeros
+    const uint32_t one2 = 0x3F803F80u;                        // bf16(1.0) x2
+    if (tid < 128) *reinterpret_cast<uint4*>(sm + S::X + (C / 8) * LF_XP + tid * 16) = make_uint4(one2, one2, one2, one2);
+    else *reinterpret_cast<uint4*>(sm + S::X + (C / 8 + 1) * LF_XP + (tid - 128) * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  const __nv_bfloat16* xb = x + (size_t)b * HW * C;
+  const float2* sb = stats + (size_t)b * HW;
+  const int r_begin = chunk * lf_chunk(HW), r_end = min(HW, r_begin + lf_chunk(HW));
+  XTile<C> xt;
+  xt.fetch(xb, sb, r_begin, tid);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const bool leader = (warp == 0) && elect_one();
+  const uint32_t smem0 = smem_u32(sm);
+  const uint32_t idesc1 = umma_idesc_bf16(128, 128, 0);
+  const uint32_t idesc2 = umma_idesc_bf16(128, C + 16, 1);     // B = x^ tile read MN-major (channels contiguous)
+  const uint32_t w_lo = umma_desc_lo(smem0 + S::W, LF_WP), x_lo = umma_desc_lo(smem0 + S::X, LF_XP);
+  const uint32_t e_lo = umma_desc_lo(smem0 + S::E, LF_TP);
+  const uint32_t xm_lo = umma_desc_lo(smem0 + S::X, 128);      // MN-major view: LBO = 8-pixel group pitch
+  const uint32_t k_hi = umma_desc_hi(128), xm_hi = umma_desc_hi(LF_XP);
+  const int quarter = warp & 3, half = warp >> 2, d = quarter * 32 + lane;
+  const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
+  const float mneg = -kmax[d];
+
+  int it = 0;
+  for (int r0 = r_begin; r0 < r_end; r0 += LF_PX, ++it) {
+    if (it > 0) mbar_wait(bar2, (it - 1) & 1, 402);            // previous S-MMAs have read the x^ and E tiles
+    xt.store(sm + S::X, tid);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (leader) {
+        issue_mmas(tmem, w_lo, k_hi, (2 * LF_WP) >> 4, x_lo, k_hi, (2 * LF_XP) >> 4, idesc1, C / 16, 0u);
+        umma_commit(bar1);
+      }
+      __syncwarp();
+    }
+    if (r0 + LF_PX < r_end) xt.fetch(xb, sb, r0 + LF_PX, tid);
+    mbar_wait(bar1, it & 1, 403);
+    tc_fence_after();
+    // e = exp(k - max) for this thread's k channel and its 64 pixels -> K-major A tile [8-pixel group][d][8]
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float v[32];
+      tmem_ld32(lane_addr + j * 32, v);
+#pragma unroll
+      for (int qq = 0; qq < 32; ++qq) v[qq] = ex2_fast(fmaf(v[qq], LF_LOG2E, mneg));
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(sm + S::E + (half * 8 + j * 4 + g) * LF_TP + d * 16) = pack_bf16x8(v + g * 8);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (leader) {
+        issue_mmas(tmem + 128u, e_lo, k_hi, (2 * LF_TP) >> 4, xm_lo, xm_hi, 256 >> 4, idesc2, LF_PX / 16, it > 0 ? 1u : 0u);
+        umma_commit(bar2);
+      }
+      __syncwarp();
+    }
+  }
+  mbar_wait(bar2, (it - 1) & 1, 404);
+  tc_fence_after();
+  if (warp < 4) {                                              // rows d = warp*32 + lane, columns [0, C] of S | rowsum
+    float* dst = part + (((size_t)b * nchunk + chunk) * 128 + d) * (C + 1);
+    const uint32_t acc = tmem + ((uint32_t)(warp * 32) << 16) + 128u;
+#pragma unroll 1
+    for (int cc = 0; cc < C / 32; ++cc) {
+      float v[32];
+      tmem_ld32(acc + cc * 32, v);
+#pragma unroll
+      for (int e = 0; e < 32; ++e) dst[cc * 32 + e] = v[e];
+    }
+    float v[32];
+    tmem_ld32(acc + C, v);                                     // column C = rowsum (the ones plane)
+    dst[C] = v[0];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, S::TMEM_COLS);
+  }
+}
+
+// =====================================================================================================
+// merge: grid = (16, B), block = 256: CTA (h, r) owns rows d = 8r .. 8r+7 of head h.
+//   ctx[d][e] = sum_c S[d][c] Wv[h*32+e][c] / (rowsum[d] HW),  Weff[c][h*32+d] = sum_e Wout[c][h*32+e] ctx[d][e],
+// written in the packed B-operand layout [16 planes][C][8].  Partial sums are added in chunk order (deterministic).
+// =====================================================================================================
+template <int C>
+__global__ void __launch_bounds__(256)
+la_merge_kernel(const float* __restrict__ part, int nchunk, const float* __restrict__ wv, const float* __restrict__ w_out,
+                __nv_bfloat16* __restrict__ weff, int HW) {
+  constexpr int R = 8;                                         // rows per CTA
+  __shared__ float Ssm[R * (C + 1)];
+  __shared__ float ctx[R * 33];
+  const int tid = threadIdx.x, h = blockIdx.x >> 2, d0 = (blockIdx.x & 3) * R, b = blockIdx.y;
+  const float* p0 = part + ((size_t)b * nchunk * 128 + h * 32 + d0) * (C + 1);
+  const size_t cstride = (size_t)128 * (C + 1);
+  for (int i = tid; i < R * (C + 1); i += 256) {               // contiguous rows d0 .. d0+7 of every chunk
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    int c = 0;
+    for (; c + 4 <= nchunk; c += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a4[u] += __ldg(p0 + (size_t)(c + u) * cstride + i);
+    }
+    for (; c < nchunk; ++c) a4[0] += __ldg(p0 + (size_t)c * cstride + i);
+    Ssm[i] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+  }
+  __syncthreads();
+  {
+    const int dd = tid >> 5, e = tid & 31;                     // 8 x 32 outputs, one per thread
+    const float* sr = Ssm + dd * (C + 1);
+    const float4* wr = reinterpret_cast<const float4*>(wv + (size_t)(h * 32 + e) * C);
+    float acc = 0.f;
+#pragma unroll 4
+    for (int c4 = 0; c4 < C / 4; ++c4) {
+      const float4 w = __ldg(wr + c4);
+      acc = fmaf(sr[4 * c4], w.x, acc);
+      acc = fmaf(sr[4 * c4 + 1], w.y, acc);
+      acc = fmaf(sr[4 * c4 + 2], w.z, acc);
+      acc = fmaf(sr[4 * c4 + 3], w.w, acc);
+    }
+    ctx[dd * 33 + e] = acc / (sr[C] * (float)HW);                // softmax normaliser and v / (h*w)
+  }
+  __syncthreads();
+  __nv_bfloat16* wdst = weff + (size_t)b * C * 128;
+  for (int i = tid; i < C * R; i += 256) {
+    const int c = i >> 3, dd = i & 7, kc = h * 32 + d0 + dd;
+    const float4* wr = reinterpret_cast<const float4*>(w_out + (size_t)c * 128 + h * 32);
+    const float* cr = ctx + dd * 33;
+    float acc = 0.f;
+#pragma unroll
+    for (int e4 = 0; e4 < 8; ++e4) {
+      const float4 w = __ldg(wr + e4);
+      acc = fmaf(w.x, cr[4 * e4], acc);
+      acc = fmaf(w.y, cr[4 * e4 + 1], acc);
+      acc = fmaf(w.z, cr[4 * e4 + 2], acc);
+      acc = fmaf(w.w, cr[4 * e4 + 3], acc);
+    }
+    wdst[(size_t)(kc >> 3) * (C * 8) + c * 8 + (kc & 7)] = __float2bfloat16_rn(acc);
+  }
+}
+
+// =====================================================================================================
+// pass 2: out = x + LN_c(Weff[b] softmax_d(Wq x^) scale + bias) * g.  grid = (nchunk, B), block = 256.
+// =====================================================================================================
+template <int C>
+struct OutSmem {
+  static constexpr int X = 0, WQ = X + (C / 8) * LF_XP, WE = WQ + (C / 8) * LF_WP, Q = WE + 16 * C * 16,
+                       PAR = Q + 16 * LF_TP, BAR = PAR + 2 * C * 4, TOTAL = BAR + 32;
+};
+
+template <int C>
+__global__ void __launch_bounds__(256, C == 64 ? 2 : 1)
+la_out_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats, const void* __restrict__ wq,
+              const __nv_bfloat16* __restrict__ weff, const float* __restrict__ bias, const float* __restrict__ gain,
+              __nv_bfloat16* __restrict__ out, int HW, float qscale, float eps) {
+  using S = OutSmem<C>;
+  extern __shared__ __align__(128) uint8_t sm[];
+  uint64_t* bar1 = reinterpret_cast<uint64_t*>(sm + S::BAR);
+  uint64_t* bar3 = bar1 + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar1 + 2);
+  float* par = reinterpret_cast<float*>(sm + S::PAR);          // [bias | gain]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  if (tid == 0) {
+    mbar_init(bar1, 1);
+    mbar_init(bar3, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  copy_g2s(sm + S::WQ, wq, (C / 8) * LF_WP, tid);
+  copy_g2s(sm + S::WE, weff + (size_t)b * C * 128, 16 * C * 16, tid);
+  for (int i = tid; i < C; i += 256) {
+    par[i] = __ldg(bias + i);
+    par[C + i] = __ldg(gain + i);
+  }
+  const __nv_bfloat16* xb = x + (size_t)b * HW * C;
+  const float2* sb = stats + (size_t)b * HW;
+  __nv_bfloat16* ob = out + (size_t)b * HW * C;
+  const int r_begin = chunk * lf_chunk(HW), r_end = min(HW, r_begin + lf_chunk(HW));
+  XTile<C> xt;
+  xt.fetch(xb, sb, r_begin, tid);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const bool leader = (warp == 0) && elect_one();
+  const uint32_t smem0 = smem_u32(sm);
+  const uint32_t idesc1 = umma_idesc_bf16(128, 128, 0), idesc3 = umma_idesc_bf16(128, C, 0);
+  const uint32_t x_lo = umma_desc_lo(smem0 + S::X, LF_XP), wq_lo = umma_desc_lo(smem0 + S::WQ, LF_WP);
+  const uint32_t q_lo = umma_desc_lo(smem0 + S::Q, LF_TP), we_lo = umma_desc_lo(smem0 + S::WE, C * 16);
+  const uint32_t k_hi = umma_desc_hi(128);
+  const int quarter = warp & 3, half = warp >> 2, px = quarter * 32 + lane;
+  const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+  const float invC = 1.f / (float)C;
+
+  int it = 0;
+  for (int r0 = r_begin; r0 < r_end; r0 += LF_PX, ++it) {
+    xt.store(sm + S::X, tid);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (leader) {
+        issue_mmas(tmem, x_lo, k_hi, (2 * LF_XP) >> 4, wq_lo, k_hi, (2 * LF_WP) >> 4, idesc1, C / 16, 0u);
+        umma_commit(bar1);
+      }
+      __syncwarp();
+    }
+    if (r0 + LF_PX < r_end) xt.fetch(xb, sb, r0 + LF_PX, tid);
+    mbar_wait(bar1, it & 1, 405);
+    tc_fence_after();
+    // per-head softmax over the 32 q channels of this thread's pixel; warp half h2 owns heads 2*h2, 2*h2+1
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int hd = half * 2 + j;
+      float v[32];
+      tmem_ld32(lane_base + hd * 32, v);
+      float m4[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+      for (int qq = 4; qq < 32; ++qq) m4[qq & 3] = fmaxf(m4[qq & 3], v[qq]);
+      const float mneg = -fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * LF_LOG2E;
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int qq = 0; qq < 32; ++qq) { v[qq] = ex2_fast(fmaf(v[qq], LF_LOG2E, mneg)); s4[qq & 3] += v[qq]; }
+      const float inv = qscale / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+#pragma unroll
+      for (int qq = 0; qq < 32; ++qq) v[qq] *= inv;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(sm + S::Q + (hd * 4 + g) * LF_TP + px * 16) = pack_bf16x8(v + g * 8);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (leader) {
+        issue_mmas(tmem + 128u, q_lo, k_hi, (2 * LF_TP) >> 4, we_lo, k_hi, (2 * C * 16) >> 4, idesc3, 8, 0u);
+        umma_commit(bar3);
+      }
+      __syncwarp();
+    }
+    if (warp < 4) {
+      const size_t row = (size_t)(r0 + px);
+      const uint4* rp = reinterpret_cast<const uint4*>(xb + row * C);
+      uint4* dp = reinterpret_cast<uint4*>(ob + row * C);
+      uint4 rq[4];                                             // residual x of the first chunk: in flight during MMA 3
+#pragma unroll
+      for (int g = 0; g < 4; ++g) rq[g] = __ldg(rp + g);
+      mbar_wait(bar3, it & 1, 406);
+      tc_fence_after();
+      const uint32_t acc = lane_base + 128u;
+      float s4[4] = {0.f, 0.f, 0.f, 0.f}, t4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int cc = 0; cc < C / 32; ++cc) {                    // pass A: LayerNorm statistics of (acc + bias)
+        float v[32];
+        tmem_ld32(acc + cc * 32, v);
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 bb = *reinterpret_cast<const float4*>(par + cc * 32 + e4 * 4);
+          const float y0 = v[e4 * 4] + bb.x, y1 = v[e4 * 4 + 1] + bb.y, y2 = v[e4 * 4 + 2] + bb.z, y3 = v[e4 * 4 + 3] + bb.w;
+          s4[0] += y0; s4[1] += y1; s4[2] += y2; s4[3] += y3;
+          t4[0] = fmaf(y0, y0, t4[0]); t4[1] = fmaf(y1, y1, t4[1]); t4[2] = fmaf(y2, y2, t4[2]); t4[3] = fmaf(y3, y3, t4[3]);
+        }
+      }
+      const float s1 = (s4[0] + s4[1]) + (s4[2] + s4[3]), s2 = (t4[0] + t4[1]) + (t4[2] + t4[3]);
+      const float mean = s1 * invC, var = fmaxf(s2 * invC - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+#pragma unroll 1
+      for (int cc = 0; cc < C / 32; ++cc) {                    // pass B: normalise, gain, + x, store
+        float v[32];
+        tmem_ld32(acc + cc * 32, v);
+        uint4 rn[4];
+        if (cc + 1 < C / 32) {                                  // next chunk's residual while this one is processed
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rn[g] = __ldg(rp + (cc + 1) * 4 + g);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float rr[8];
+          unpack_bf16x8(rq[g], rr);
+          const float4 b0 = *reinterpret_cast<const float4*>(par + cc * 32 + g * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(par + cc * 32 + g * 8 + 4);
+          const float4 g0 = *reinterpret_cast<const float4*>(par + C + cc * 32 + g * 8);
+          const float4 g1 = *reinterpret_cast<const float4*>(par + C + cc * 32 + g * 8 + 4);
+          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) rr[e] = fmaf((v[g * 8 + e] + bv[e] - mean) * rstd, gv[e], rr[e]);
+          dp[cc * 4 + g] = pack_bf16x8(rr);
+        }
+        if (cc + 1 < C / 32) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rq[g] = rn[g];
+        }
+      }
+    }
+    tc_fence_before();            // the barrier at the top of the next tile orders these TMEM reads before its MMAs
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+template <int C>
+static int launch_fused(const void* x, const float* stats, const void* wq, const void* wk, const float* wv,
+                        const float* w_out, const float* bias, const float* gain, void* weff, void* out, float* scratch,
+                        int B, int HW, float qscale, float eps, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(la_kmax_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, KmaxSmem<C>::TOTAL);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(la_ctx_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtxSmem<C>::TOTAL);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(la_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, OutSmem<C>::TOTAL);
+    if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "linattn_fused attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  const int nchunk = (HW + lf_chunk(HW) - 1) / lf_chunk(HW);
+  float* part = scratch;
+  float* pmax = scratch + (size_t)B * nchunk * 128 * (C + 1);
+  const dim3 grid((unsigned)nchunk, (unsigned)B);
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  const float2* sb = reinterpret_cast<const float2*>(stats);
+  la_kmax_kernel<C><<<grid, 256, KmaxSmem<C>::TOTAL, st>>>(xb, sb, wk, pmax, HW);
+  if (int rc = check_launch("la_kmax")) return rc;
+  la_ctx_kernel<C><<<grid, 256, CtxSmem<C>::TOTAL, st>>>(xb, sb, wk, pmax, part, HW);
+  if (int rc = check_launch("la_ctx")) return rc;
+  la_merge_kernel<C><<<dim3(16, (unsigned)B), 256, 0, st>>>(part, nchunk, wv, w_out, reinterpret_cast<__nv_bfloat16*>(weff), HW);
+  if (int rc = check_launch("la_merge")) return rc;
+  la_out_kernel<C><<<grid, 256, OutSmem<C>::TOTAL, st>>>(xb, sb, wq, reinterpret_cast<const __nv_bfloat16*>(weff), bias, gain,
+                                                         reinterpret_cast<__nv_bfloat16*>(out), HW, qscale, eps);
+  return check_launch("la_out");
+}
+
+}  // namespace idiff
+
+extern "C" {
+using namespace idiff;
+
+size_t idiff_linattn_fused_scratch_floats(int B, int HW, int C) {
+  const size_t nchunk = (size_t)(HW + lf_chunk(HW) - 1) / lf_chunk(HW);
+  return (size_t)B * nchunk * (128 * (size_t)(C + 1) + 128);   // S | rowsum partials + per-chunk channel maxima
+}
+
+int idiff_linattn_fused(const void* x, const float* row_stats, const void* wq_packed, const void* wk_packed,
+                        const float* wv, const float* w_out, const float* bias_out, const float* gain_out,
+                        void* weff_scratch, void* out, float* scratch, int B, int HW, int C, float qscale, float ln_eps,
+                        void* stream) {
+  IDIFF_REQUIRE(x && row_stats && wq_packed && wk_packed && wv && w_out && bias_out && gain_out && weff_scratch && out &&
+                    scratch && B > 0 && HW > 0, "linattn_fused: bad arguments");
+  IDIFF_REQUIRE(C == 64 || C == 128, "linattn_fused: C must be 64 or 128 (got %d)", C);
+  IDIFF_REQUIRE(HW % LF_PX == 0, "linattn_fused: H*W must be a multiple of %d", LF_PX);
+  IDIFF_REQUIRE(aligned16(x) && aligned16(out) && aligned16(wq_packed) && aligned16(wk_packed) && aligned16(weff_scratch) &&
+                    (reinterpret_cast<uintptr_t>(row_stats) & 7u) == 0, "linattn_fused: alignment");
+  if (C == 64)
+    return launch_fused<64>(x, row_stats, wq_packed, wk_packed, wv, w_out, bias_out, gain_out, weff_scratch, out, scratch, B,
+                            HW, qscale, ln_eps, as_stream(stream));
+  return launch_fused<128>(x, row_stats, wq_packed, wk_packed, wv, w_out, bias_out, gain_out, weff_scratch, out, scratch, B,
+                           HW, qscale, ln_eps, as_stream(stream));
+}
+
+}  // extern "C"

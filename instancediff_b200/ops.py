@@ -165,3 +165,23 @@ def self_attention(qkv, heads, scale):
     check(_lib.lib().idiff_self_attention(qkv.data_ptr(), out.data_ptr(), B, Lq, heads, scale, _s(qkv)),
           "self_attention")
     return out
+
+
+def linattn_fused(x, row_stats, wqkv, g_pre, w_out, b_out, g_out, eps=1e-5):
+    """Residual(PreNorm(LinearAttention)) for C = 64 / 128 in three fused passes.  x: bf16 [B,H,W,C]; row_stats: fp32
+    [B*H*W, 2] (mean, rstd) of x; wqkv [384, C]; g_pre [C]; w_out [C, 128]; b_out, g_out [C]."""
+    from .packing import pack_conv_weight
+    B, H, W, Cc = x.shape
+    L = _lib.lib()
+    wg = wqkv.float() * g_pre.float()[None, :]
+    wq = pack_conv_weight(wg[0:128], 128).to(x.device)
+    wk = pack_conv_weight(wg[128:256], 128).to(x.device)
+    wv = wg[256:384].contiguous().to(x.device)
+    weff = torch.empty(B, Cc * 128, dtype=torch.bfloat16, device=x.device)
+    scratch = torch.empty(L.idiff_linattn_fused_scratch_floats(B, H * W, Cc), dtype=torch.float32, device=x.device)
+    out = torch.empty_like(x)
+    check(L.idiff_linattn_fused(x.data_ptr(), row_stats.data_ptr(), wq.data_ptr(), wk.data_ptr(), wv.data_ptr(),
+                                w_out.float().contiguous().data_ptr(), b_out.float().contiguous().data_ptr(),
+                                g_out.float().contiguous().data_ptr(), weff.data_ptr(), out.data_ptr(),
+                                scratch.data_ptr(), B, H * W, Cc, 32 ** -0.5, eps, _s(x)), "linattn_fused")
+    return out

@@ -141,6 +141,7 @@ class ConditionalUNet:
         self.params: Dict[str, torch.Tensor] = {}
         self._plans: Dict[tuple, "_Plan"] = {}
         self._ctx_key = None
+        self._ctx_ref = None
         self._crossvec: Dict[tuple, torch.Tensor] = {}
         self._init_params(seed)
         self._pack()
@@ -220,6 +221,11 @@ class ConditionalUNet:
                 e["wsum"] = f32(wsum)
                 pk[f + ".to_out"] = dict(w_f32=f32(P[f + ".to_out.weight"].reshape(dim, 128)),
                                          bias=f32(P[f + ".to_out.bias"]), g=f32(P[f + ".out_norm.g"].reshape(-1)))
+                if dim in (64, 128):                  # fused three-pass kernel: q / k weights packed separately,
+                    wg = wq * g_pre[None, :]          # v folded into the merge step (pre-norm gain in the weights)
+                    pk[f + ".fused"] = dict(wq=pack_conv_weight(wg[0:128], 128).to(self.device),
+                                            wk=pack_conv_weight(wg[128:256], 128).to(self.device),
+                                            wv=f32(wg[256:384]))
             else:
                 pk[prefix + ".prenorm"] = dict(g=f32(g_pre))
                 pk[f + ".norm"] = dict(g=f32(P[f + ".norm.weight"]), b=f32(P[f + ".norm.bias"]))
@@ -291,12 +297,15 @@ class ConditionalUNet:
     def set_image_context(self, ctx: torch.Tensor):
         """Cross-attention to ONE context token: softmax == 1, so CrossAttn(x, ctx) = Wo (Wv ctx) + bo for
         every pixel and every step (App. A) -- computed once per embedding, added as a per-image bias."""
+        ctx_arg = ctx                                  # the caller's tensor object (identity of the embedding)
         if ctx.dim() == 3:
             if ctx.shape[1] != 1:
                 raise _lib.IdiffError("image_context must hold one token per image ([B,1,D] or [B,D])")
             ctx = ctx[:, 0]
+        # identity of the embedding tensor: the tensor itself is kept alive in self._ctx_ref, otherwise the caching
+        # allocator may hand its address to the NEXT embedding (same pointer, version and shape -> stale context)
         key = (ctx.data_ptr(), ctx._version, tuple(ctx.shape))
-        if key == self._ctx_key:
+        if key == self._ctx_key and self._ctx_ref is ctx_arg:
             return
         c = ctx.detach().to(self.device, torch.float32).contiguous()
         B, D = c.shape
@@ -312,6 +321,7 @@ class ConditionalUNet:
             check(self.L.idiff_cross_vec(c.data_ptr(), wv.data_ptr(), wo.data_ptr(), bo.data_ptr(), buf.data_ptr(),
                                          B, D, wo.shape[0], s), "cross_vec")
         self._ctx_key = key
+        self._ctx_ref = ctx_arg
         for plan in self._plans.values():
             if plan.B == B:
                 plan.bind_context(self._crossvec)
@@ -377,6 +387,7 @@ class _Plan:
         self.dev = net.device
         self.ops: List = []
         self.op_info: List[tuple] = []        # (kernel kind, algorithmic FLOPs, label) parallel to self.ops
+        self.op_bytes: Dict[int, float] = {}  # op index -> algorithmic HBM bytes (conv_gemm launches)
         self.keep: List = []
         self.scratch: Dict[tuple, torch.Tensor] = {}
         self.ctx_slots: Dict[str, GemmParams] = {}
@@ -437,6 +448,13 @@ class _Plan:
         L, ref = self.L, C.byref(p)
         self.ops.append(lambda s: check(L.idiff_conv_gemm(ref, s), "conv_gemm"))
         flops = 2.0 * self.B * out.H * out.W * p.N * (p.cin0 + p.cin1) * k * k
+        # algorithmic HBM bytes: every source pixel once, every output element once, residuals once (bf16)
+        px_out = self.B * out.H * out.W
+        px_in = px_out * (stride * stride) // (4 if up else 1)
+        out_cols = p.N // 2 if epi == EPI_GEGLU else p.N
+        nbytes = 2.0 * (px_in * (p.cin0 + p.cin1) + px_out * out_cols
+                        + px_out * p.N * ((res0 is not None) + (res1 is not None)))
+        self.op_bytes[len(self.ops) - 1] = nbytes
         self.op_info.append(("conv_gemm", flops, f"k{k}s{stride}u{up} {p.cin0 + p.cin1}->{p.N} @{out.H}x{out.W}"))
         self.n_launch += 1
 
@@ -498,13 +516,30 @@ class _Plan:
     def linear_attn(self, prefix, x: _Act) -> _Act:
         pk, B, H, W, Cc, L = self.net.pk, self.B, x.H, x.W, x.C, self.L
         f = prefix + ".fn"
+        to = pk[f + ".to_out"]
+        if (f + ".fused") in pk and (H * W) % 128 == 0:
+            # q, k, v never touch HBM: k-max, context and output passes read x directly (csrc/linattn_fused.cu)
+            fu = pk[f + ".fused"]
+            weff = self.tmp("la_weff", (B, Cc * 128))
+            nfl = L.idiff_linattn_fused_scratch_floats(B, H * W, Cc)
+            scratch = self.tmp("laf_scratch", (nfl,), torch.float32)
+            out = self.act(H, W, Cc)
+            args = (_ptr(x.t), _ptr(x.stats), _ptr(fu["wq"]), _ptr(fu["wk"]), _ptr(fu["wv"]), _ptr(to["w_f32"]),
+                    _ptr(to["bias"]), _ptr(to["g"]), _ptr(weff), _ptr(out.t), _ptr(scratch), B, H * W, Cc, 32 ** -0.5, 1e-5)
+            self.ops.append(lambda s: check(L.idiff_linattn_fused(*args, s), "linattn_fused"))
+            # algorithmic work: q and k projections, e * x^ context, q * Weff output
+            flops = 2.0 * B * H * W * (2 * 128 * Cc + 128 * (Cc + 16) + 128 * Cc)
+            self.op_info.append(("linattn_fused", flops, f"C{Cc} @{H}x{W}"))
+            self.op_bytes[len(self.ops) - 1] = 2.0 * B * H * W * Cc * 4 + 8.0 * B * H * W * 3   # 3 reads + 1 write + stats
+            self.n_launch += 4
+            self.named[prefix] = out
+            return out
         qkv = self.act(H, W, 384, tmp_name="la_qkv")
         self.gemm(x, None, pk[f + ".to_qkv"], qkv, k=1, bias=False, row_stats=x.stats, epi=EPI_QSOFTMAX,
                   qscale=32 ** -0.5)
         weff = self.tmp("la_weff", (B, Cc * 128))
         nfl = L.idiff_linattn_scratch_floats(B, H * W)
         scratch = self.tmp("la_scratch", (nfl,), torch.float32)
-        to = pk[f + ".to_out"]
         args = (_ptr(qkv.t), _ptr(to["w_f32"]), _ptr(weff), _ptr(scratch), B, H * W, Cc)
         self.ops.append(lambda s: check(L.idiff_linattn_context(*args, s), "linattn_context"))
         self.op_info.append(("linattn_context", 2.0 * 2 * B * H * W * 128 * 32, f"C{Cc} @{H}x{W}"))
@@ -612,15 +647,17 @@ class _Plan:
 
     def run_timed(self, xt, cond, t_scalar, reps=3):
         """Instrumented replay (bench/profiling): CUDA events around every launch on the launching stream.
-        Returns [(kind, label, flops, mean_ms)] including the time-embedding and stem launches."""
+        Returns [(kind, label, flops, mean_ms, algorithmic_bytes)] including the time-embedding and stem launches."""
         L = self.L
         stream = torch.cuda.current_stream(self.dev)
         s = stream.cuda_stream
         calls = [("time_embed", "", 0.0, lambda: check(L.idiff_time_embed(None, t_scalar, *self._time_args, s))),
                  ("stem_conv7", f"@{self.H}x{self.W}", 2.0 * self.B * self.H * self.W * 98 * self.net.nf,
                   lambda: check(L.idiff_stem_conv7_tc(xt.data_ptr(), cond.data_ptr(), *self._stem_tail, s)))]
-        for op, (kind, flops, label) in zip(self.ops, self.op_info):
+        nbytes = [0.0, 4.0 * self.B * self.H * self.W * 2 + 2.0 * self.B * self.H * self.W * self.net.nf]
+        for i, (op, (kind, flops, label)) in enumerate(zip(self.ops, self.op_info)):
             calls.append((kind, label, flops, (lambda op=op: op(s))))
+            nbytes.append(self.op_bytes.get(i, 0.0))
         acc = [0.0] * len(calls)
         for _ in range(reps):
             evs = []
@@ -633,7 +670,7 @@ class _Plan:
             torch.cuda.synchronize(self.dev)
             for i, (e0, e1) in enumerate(evs):
                 acc[i] += e0.elapsed_time(e1)
-        return [(k, lbl, fl, a / reps) for (k, lbl, fl, _), a in zip(calls, acc)]
+        return [(k, lbl, fl, a / reps, nb) for (k, lbl, fl, _), a, nb in zip(calls, acc, nbytes)]
 
     def run(self, xt, cond, t_dev, t_scalar):
         L = self.L

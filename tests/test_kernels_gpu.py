@@ -167,3 +167,38 @@ def test_self_attention(L):
             msgs.append(f"debug flags {flags}: rel_err={rel_err(o2, ref):.4g}")
         _lib.lib().idiff_set_debug_flags(0)
         pytest.fail("\n".join(msgs))
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 64, 64, 64), (2, 32, 32, 128), (1, 128, 128, 64)])
+def test_linattn_fused_matches_reference(shape):
+    """Three-pass fused linear attention (q, k, v never in HBM) vs the fp32 module math of SURVEY App. A:
+    x + LN_c(to_out(ctx^T q)) with q = softmax_d * scale, k = softmax_n, v / HW, x^ = ChanLayerNorm(x) * g."""
+    from instancediff_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    B, H, W, Cc = shape
+    x = rand_act(B, H, W, Cc, g)
+    xf = x.float()
+    mean, var = xf.mean(-1, keepdim=True), xf.var(-1, unbiased=False, keepdim=True)
+    rstd = torch.rsqrt(var + 1e-5)
+    stats = torch.cat([mean, rstd], -1).reshape(-1, 2).contiguous()
+    g_pre = (torch.rand(Cc, generator=g) + 0.5).cuda()
+    wqkv = ((torch.rand(384, Cc, generator=g) * 2 - 1) * (2.0 / Cc ** 0.5)).cuda()
+    w_out = ((torch.rand(Cc, 128, generator=g) * 2 - 1) / 128 ** 0.5).cuda()
+    b_out = (torch.rand(Cc, generator=g) - 0.5).cuda()
+    g_out = (torch.rand(Cc, generator=g) + 0.5).cuda()
+    out = ops.linattn_fused(x, stats, wqkv, g_pre, w_out, b_out, g_out)
+    torch.cuda.synchronize()
+    xn = (xf - mean) * rstd * g_pre
+    qkv = xn.reshape(B, H * W, Cc) @ wqkv.t()                          # [B, N, 384]
+    q, k, v = (t.reshape(B, H * W, 4, 32).permute(0, 2, 3, 1) for t in qkv.chunk(3, dim=-1))   # [B, h, d, N]
+    q = q.softmax(dim=-2) * 32 ** -0.5
+    k = k.softmax(dim=-1)
+    v = v / (H * W)
+    ctx = torch.einsum("bhdn,bhen->bhde", k, v)
+    o = torch.einsum("bhde,bhdn->bhen", ctx, q).reshape(B, 128, H * W).permute(0, 2, 1)       # [B, N, 128]
+    y = o @ w_out.t() + b_out
+    y = (y - y.mean(-1, keepdim=True)) * torch.rsqrt(y.var(-1, unbiased=False, keepdim=True) + 1e-5) * g_out
+    ref = xf + y.reshape(B, H, W, Cc)
+    assert rel_err(out, ref) <= 1e-2, describe(out, ref, "linattn fused")
+    # the attention branch alone (without the dominating residual) must match as well
+    assert rel_err(out.float() - xf, ref - xf) <= 3e-2, describe(out.float() - xf, ref - xf, "linattn branch")
