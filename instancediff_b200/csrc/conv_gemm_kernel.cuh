@@ -818,19 +818,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           uint32_t b_lo = b_res;
 #pragma unroll 1
           for (int dy = 0; dy < KS; ++dy) {
-#pragma unroll 1
-            for (int dx = 0; dx < KS; ++dx) {
-              if (leader) {
+            // one filter row (KS taps = 4*KS MMAs) per iteration under a single leader branch: the row's tap
+            // offsets are immediates, the loop overhead is paid once per row
+            if (leader) {
+#pragma unroll
+              for (int dx = 0; dx < KS; ++dx) {
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                  umma_bf16_lohi(tacc, a_lo + (uint32_t)((kk * 2 * G::LBO) >> 4), a_hi,
-                                 b_lo + (uint32_t)((kk * 2 * lboB) >> 4), b_hi, idesc, kk == 0 ? accum : 1u);
+                  umma_bf16_lohi(tacc, a_lo + (uint32_t)(G::slot(0, dx) - G::slot(0, 0)) + (uint32_t)((kk * 2 * G::LBO) >> 4), a_hi,
+                                 b_lo + (uint32_t)((dx * stageB) >> 4) + (uint32_t)((kk * 2 * lboB) >> 4), b_hi, idesc,
+                                 (dx | kk) == 0 ? accum : 1u);
               }
-              accum = 1u;
-              a_lo += (uint32_t)(G::slot(0, dx + 1) - G::slot(0, dx));      // next tap of this row (compile time per dx
-              b_lo += (uint32_t)(stageB >> 4);                              //  only through the unrolled kk loop)
             }
-            a_lo += (uint32_t)(G::slot(1, 0) - G::slot(0, KS));
+            accum = 1u;
+            a_lo += (uint32_t)(G::slot(1, 0) - G::slot(0, 0));
+            b_lo += (uint32_t)((KS * stageB) >> 4);
           }
           b_res = b_lo;
           PROF_ADD(8, tp);

@@ -39,10 +39,10 @@ IDIFF_DEVINL float ex2_fast(float x) {
 }
 
 // ---- x^ tile loader: 128 pixels x C channels -> [C/8 planes][128 px][8 ch], normalised on the way ------------
-template <int C>
+template <int C, int NT = 256>
 struct XTile {
   static constexpr int TPP = C / 8;              // threads (16 B vectors) per pixel
-  static constexpr int PPS = 256 / TPP;          // pixels per sweep of the 256 threads
+  static constexpr int PPS = NT / TPP;           // pixels per sweep of the NT loading threads
   static constexpr int NV = LF_PX / PPS;         // vectors per thread
   uint4 q[NV];
   float2 st[NV];
@@ -361,6 +361,11 @@ struct OutSmem {
                        PAR = Q + 16 * LF_TP, BAR = PAR + 2 * C * 4, TOTAL = BAR + 32;
 };
 
+// Two warp groups per CTA, pipelined across tiles through mbarriers:
+//   front (warps 4-7): x^ tile -> smem, q GEMM, per-head softmax of its pixel row (4 heads), q tile -> smem, out GEMM
+//   back  (warps 0-3): channel LayerNorm + gain + residual + store of the PREVIOUS tile's out accumulator
+// so the LayerNorm epilogue of tile i-1 overlaps the q GEMM / softmax of tile i (the single-group version spent
+// 33 % of its samples in bar.sync with half the warps idle during the output epilogue).
 template <int C>
 __global__ void __launch_bounds__(256, C == 64 ? 2 : 1)
 la_out_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats, const void* __restrict__ wq,
@@ -368,15 +373,17 @@ la_out_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ st
               __nv_bfloat16* __restrict__ out, int HW, float qscale, float eps) {
   using S = OutSmem<C>;
   extern __shared__ __align__(128) uint8_t sm[];
-  uint64_t* bar1 = reinterpret_cast<uint64_t*>(sm + S::BAR);
-  uint64_t* bar3 = bar1 + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar1 + 2);
+  uint64_t* bar1 = reinterpret_cast<uint64_t*>(sm + S::BAR);   // q accumulator complete
+  uint64_t* bar3 = bar1 + 1;                                    // out accumulator complete (q tile and x^ tile read)
+  uint64_t* acc3_free = bar1 + 2;                               // back group has read the out accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar1 + 3);
   float* par = reinterpret_cast<float*>(sm + S::PAR);          // [bias | gain]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int chunk = blockIdx.x, b = blockIdx.y;
   if (tid == 0) {
     mbar_init(bar1, 1);
     mbar_init(bar3, 1);
+    mbar_init(acc3_free, 4);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 256);
@@ -390,81 +397,89 @@ la_out_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ st
   const float2* sb = stats + (size_t)b * HW;
   __nv_bfloat16* ob = out + (size_t)b * HW * C;
   const int r_begin = chunk * lf_chunk(HW), r_end = min(HW, r_begin + lf_chunk(HW));
-  XTile<C> xt;
-  xt.fetch(xb, sb, r_begin, tid);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const bool leader = (warp == 0) && elect_one();
-  const uint32_t smem0 = smem_u32(sm);
-  const uint32_t idesc1 = umma_idesc_bf16(128, 128, 0), idesc3 = umma_idesc_bf16(128, C, 0);
-  const uint32_t x_lo = umma_desc_lo(smem0 + S::X, LF_XP), wq_lo = umma_desc_lo(smem0 + S::WQ, LF_WP);
-  const uint32_t q_lo = umma_desc_lo(smem0 + S::Q, LF_TP), we_lo = umma_desc_lo(smem0 + S::WE, C * 16);
-  const uint32_t k_hi = umma_desc_hi(128);
-  const int quarter = warp & 3, half = warp >> 2, px = quarter * 32 + lane;
+  const int quarter = warp & 3, px = quarter * 32 + lane;
   const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
-  const float invC = 1.f / (float)C;
 
-  int it = 0;
-  for (int r0 = r_begin; r0 < r_end; r0 += LF_PX, ++it) {
-    xt.store(sm + S::X, tid);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-      tc_fence_after();
-      if (leader) {
-        issue_mmas(tmem, x_lo, k_hi, (2 * LF_XP) >> 4, wq_lo, k_hi, (2 * LF_WP) >> 4, idesc1, C / 16, 0u);
-        umma_commit(bar1);
+  if (warp >= 4) {
+    // ------------------------------------------------ front group ------------------------------------------
+    const int ftid = tid - 128;
+    const bool leader = (warp == 4) && elect_one();
+    const uint32_t smem0 = smem_u32(sm);
+    const uint32_t idesc1 = umma_idesc_bf16(128, 128, 0), idesc3 = umma_idesc_bf16(128, C, 0);
+    const uint32_t x_lo = umma_desc_lo(smem0 + S::X, LF_XP), wq_lo = umma_desc_lo(smem0 + S::WQ, LF_WP);
+    const uint32_t q_lo = umma_desc_lo(smem0 + S::Q, LF_TP), we_lo = umma_desc_lo(smem0 + S::WE, C * 16);
+    const uint32_t k_hi = umma_desc_hi(128);
+    XTile<C, 128> xt;
+    xt.fetch(xb, sb, r_begin, ftid);
+    int it = 0;
+    for (int r0 = r_begin; r0 < r_end; r0 += LF_PX, ++it) {
+      xt.store(sm + S::X, ftid);                                // x^ tile free: bar1 of the previous tile was waited
+      fence_proxy_async_smem();
+      tc_fence_before();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 4) {
+        tc_fence_after();
+        if (leader) {
+          issue_mmas(tmem, x_lo, k_hi, (2 * LF_XP) >> 4, wq_lo, k_hi, (2 * LF_WP) >> 4, idesc1, C / 16, 0u);
+          umma_commit(bar1);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-    }
-    if (r0 + LF_PX < r_end) xt.fetch(xb, sb, r0 + LF_PX, tid);
-    mbar_wait(bar1, it & 1, 405);
-    tc_fence_after();
-    // per-head softmax over the 32 q channels of this thread's pixel; warp half h2 owns heads 2*h2, 2*h2+1
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int hd = half * 2 + j;
-      float v[32];
-      tmem_ld32(lane_base + hd * 32, v);
-      float m4[4] = {v[0], v[1], v[2], v[3]};
-#pragma unroll
-      for (int qq = 4; qq < 32; ++qq) m4[qq & 3] = fmaxf(m4[qq & 3], v[qq]);
-      const float mneg = -fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * LF_LOG2E;
-      float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int qq = 0; qq < 32; ++qq) { v[qq] = ex2_fast(fmaf(v[qq], LF_LOG2E, mneg)); s4[qq & 3] += v[qq]; }
-      const float inv = qscale / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
-#pragma unroll
-      for (int qq = 0; qq < 32; ++qq) v[qq] *= inv;
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        *reinterpret_cast<uint4*>(sm + S::Q + (hd * 4 + g) * LF_TP + px * 16) = pack_bf16x8(v + g * 8);
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
+      if (r0 + LF_PX < r_end) xt.fetch(xb, sb, r0 + LF_PX, ftid);
+      mbar_wait(bar1, it & 1, 405);
       tc_fence_after();
-      if (leader) {
-        issue_mmas(tmem + 128u, q_lo, k_hi, (2 * LF_TP) >> 4, we_lo, k_hi, (2 * C * 16) >> 4, idesc3, 8, 0u);
-        umma_commit(bar3);
+      if (it > 0) mbar_wait(bar3, (it - 1) & 1, 407);           // previous out GEMM has read the q tile
+      // per-head softmax over the 32 q channels of this thread's pixel
+#pragma unroll 1
+      for (int hd = 0; hd < 4; ++hd) {
+        float v[32];
+        tmem_ld32(lane_base + hd * 32, v);
+        float m4[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+        for (int qq = 4; qq < 32; ++qq) m4[qq & 3] = fmaxf(m4[qq & 3], v[qq]);
+        const float mneg = -fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * LF_LOG2E;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int qq = 0; qq < 32; ++qq) { v[qq] = ex2_fast(fmaf(v[qq], LF_LOG2E, mneg)); s4[qq & 3] += v[qq]; }
+        const float inv = qscale / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+#pragma unroll
+        for (int qq = 0; qq < 32; ++qq) v[qq] *= inv;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(sm + S::Q + (hd * 4 + g) * LF_TP + px * 16) = pack_bf16x8(v + g * 8);
       }
-      __syncwarp();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 4) {
+        if (it > 0) mbar_wait(acc3_free, (it - 1) & 1, 408);    // back group is done with the out accumulator
+        tc_fence_after();
+        if (leader) {
+          issue_mmas(tmem + 128u, q_lo, k_hi, (2 * LF_TP) >> 4, we_lo, k_hi, (2 * C * 16) >> 4, idesc3, 8, 0u);
+          umma_commit(bar3);
+        }
+        __syncwarp();
+      }
     }
-    if (warp < 4) {
+  } else {
+    // ------------------------------------------------ back group -------------------------------------------
+    const float invC = 1.f / (float)C;
+    const uint32_t acc = lane_base + 128u;
+    int it = 0;
+    for (int r0 = r_begin; r0 < r_end; r0 += LF_PX, ++it) {
       const size_t row = (size_t)(r0 + px);
       const uint4* rp = reinterpret_cast<const uint4*>(xb + row * C);
       uint4* dp = reinterpret_cast<uint4*>(ob + row * C);
-      uint4 rq[4];                                             // residual x of the first chunk: in flight during MMA 3
+      uint4 rq[4];                                             // residual x of the first chunk: in flight during the wait
 #pragma unroll
       for (int g = 0; g < 4; ++g) rq[g] = __ldg(rp + g);
       mbar_wait(bar3, it & 1, 406);
       tc_fence_after();
-      const uint32_t acc = lane_base + 128u;
       float s4[4] = {0.f, 0.f, 0.f, 0.f}, t4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int cc = 0; cc < C / 32; ++cc) {                    // pass A: LayerNorm statistics of (acc + bias)
@@ -485,6 +500,11 @@ la_out_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ st
       for (int cc = 0; cc < C / 32; ++cc) {                    // pass B: normalise, gain, + x, store
         float v[32];
         tmem_ld32(acc + cc * 32, v);
+        if (cc == C / 32 - 1) {                                 // last TMEM read: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc3_free);
+        }
         uint4 rn[4];
         if (cc + 1 < C / 32) {                                  // next chunk's residual while this one is processed
 #pragma unroll
@@ -510,7 +530,6 @@ la_out_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ st
         }
       }
     }
-    tc_fence_before();            // the barrier at the top of the next tile orders these TMEM reads before its MMAs
   }
   tc_fence_before();
   __syncthreads();
