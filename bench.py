@@ -274,6 +274,24 @@ def run_cuda(args):
     torch.cuda.synchronize(dev)
     sde_us = e0.elapsed_time(e1) / 50 * 1e3
     sde_gbs = 16.0 * n_el / (sde_us * 1e-6) / 1e9
+    # The B=32 state (4 x 8.4 MB) is an 8 us launch that lives in the 126 MB L2.  The same kernel on the B=256 state of
+    # BASELINE config 3 (268 MB of traffic per launch, larger than L2) shows what it reaches against HBM.
+    n_big = 8 * n_el
+    xb, eb, mb = (torch.randn(n_big, device=dev) for _ in range(3))
+
+    def sde_big():
+        _lib.check(_lib.lib().idiff_sde_step(xb.data_ptr(), xb.data_ptr(), eb.data_ptr(), mb.data_ptr(), None,
+                                             row.data_ptr(), 0, 1, 1, 0, n_big, s_ptr), "sde_step")
+    for _ in range(3):
+        sde_big()
+    e0.record()
+    for _ in range(20):
+        sde_big()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    sde_big_us = e0.elapsed_time(e1) / 20 * 1e3
+    sde_big_gbs = 16.0 * n_big / (sde_big_us * 1e-6) / 1e9
+    del xb, eb, mb
 
     launches_per_fwd = plan.n_launch
     gpu_launches = args.steps * (T_STEPS * (launches_per_fwd + 2) + 0)
@@ -314,7 +332,10 @@ def run_cuda(args):
                                 "tflops": split["1x1"]["flops"] / (split["1x1"]["ms"] / 1e3) / 1e12,
                                 "launches_per_forward": split["1x1"]["n"], "ms_per_forward": split["1x1"]["ms"]},
         "roofline_sde": {"bound": "hbm", "kernel": "sde_step_kernel", "achieved": sde_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                         "frac": sde_gbs / pk["hbm"], "us_per_launch": sde_us, "bytes_per_element": 16},
+                         "frac": sde_gbs / pk["hbm"], "us_per_launch": sde_us, "bytes_per_element": 16,
+                         "at_batch_256": {"elements": n_big, "us_per_launch": sde_big_us, "achieved": sde_big_gbs,
+                                          "frac": sde_big_gbs / pk["hbm"],
+                                          "note": "same kernel on the B=256 state (268 MB per launch, exceeds L2)"}},
         "forward_breakdown_ms": {k: round(v["ms"], 4) for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1]["ms"])},
         "forward_ms_sum_of_kernels": fwd_ms,
     }
@@ -343,7 +364,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--cpu-steps", type=int, default=8, help="SDE steps of the bounded CPU baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=48, help="SDE steps of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-kernels", default=None, help="write the per-launch timing table (CSV) here")
     args = ap.parse_args()

@@ -49,23 +49,28 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  // tile loader: 128 rows x 32 channels -> [4 planes][128 rows][8]; rows >= L are zero
-  auto load_tile = [&](int smem_off, int row0, int col_off) {
-    const int c8 = tid & 3;
-    uint4 q[4];
+  // tile loader: 128 rows x 32 channels -> [4 planes][128 rows][8]; rows >= L are zero.  Split into a register
+  // fetch and a shared-memory store so the NEXT key block's K / V tiles are in flight while this one is processed.
+  const int lc8 = tid & 3, lrow = tid >> 2;
+  auto fetch_tile = [&](uint4* q, int row0, int col_off) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {                       // branch-free: clamped row, zeroed afterwards
-      const int row = row0 + (tid >> 2) + 32 * i;
+      const int row = row0 + lrow + 32 * i;
       const int rc = row < L ? row : L - 1;
-      q[i] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)rc * ld + col_off + c8 * 8));
+      q[i] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)rc * ld + col_off + lc8 * 8));
       if (row >= L) q[i] = make_uint4(0u, 0u, 0u, 0u);
     }
+  };
+  auto store_tile = [&](int smem_off, const uint4* q) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      *reinterpret_cast<uint4*>(sm + smem_off + c8 * AT_PLANE + ((tid >> 2) + 32 * i) * 16) = q[i];
+      *reinterpret_cast<uint4*>(sm + smem_off + lc8 * AT_PLANE + (lrow + 32 * i) * 16) = q[i];
   };
-
-  load_tile(AT_Q, q0, 0);
+  {
+    uint4 qq[4];
+    fetch_tile(qq, q0, 0);
+    store_tile(AT_Q, qq);
+  }
 
   const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);
   const uint32_t idesc_o = umma_idesc_bf16(128, 32, 1);          // B (= V) is MN-major
@@ -87,10 +92,13 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
   float m_run = -INFINITY, l_run = 0.f;
 
   const int nblk = (L + 127) / 128;
+  uint4 kq[4], vq[4];
+  fetch_tile(kq, 0, C);
+  fetch_tile(vq, 0, 2 * C);
   for (int j = 0; j < nblk; ++j) {
     const int k0 = j * 128;
-    load_tile(AT_K, k0, C);
-    load_tile(AT_V, k0, 2 * C);
+    store_tile(AT_K, kq);
+    store_tile(AT_V, vq);
     fence_proxy_async_smem();
     __syncthreads();
     if (warp == 0) {
@@ -104,17 +112,29 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
       }
       __syncwarp();
     }
+    if (j + 1 < nblk) {                                          // next block's tiles: in flight during softmax + PV
+      fetch_tile(kq, k0 + 128, C);
+      fetch_tile(vq, k0 + 128, 2 * C);
+    }
     mbar_wait(bar_s, j & 1, 201);
     tc_fence_after();
+    const bool full = k0 + 128 <= L;                             // no key masking needed in this block
 
     // ---- online softmax over this key block (scores scaled by 1/sqrt(d), in log2 domain) ----
     float mx = -INFINITY;
     for (int cc = 0; cc < 4; ++cc) {
       float v[32];
       tmem_ld32(lane_addr + cc * 32, v);
+      if (full) {
+        float m4[4] = {v[0], v[1], v[2], v[3]};
 #pragma unroll
-      for (int q = 0; q < 32; ++q)
-        if (k0 + cc * 32 + q < L) mx = fmaxf(mx, v[q]);
+        for (int q = 4; q < 32; ++q) m4[q & 3] = fmaxf(m4[q & 3], v[q]);
+        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+          if (k0 + cc * 32 + q < L) mx = fmaxf(mx, v[q]);
+      }
     }
     const float m_new = fmaxf(m_run, mx * scale_log2e);
     const float alpha = exp2f(m_run - m_new);                    // exp2f(-inf) = 0 on the first block
@@ -122,11 +142,23 @@ self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
     for (int cc = 0; cc < 4; ++cc) {
       float v[32];
       tmem_ld32(lane_addr + cc * 32, v);
+      if (full) {
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        const float pv = (k0 + cc * 32 + q < L) ? exp2f(fmaf(v[q], scale_log2e, -m_new)) : 0.f;
-        v[q] = pv;
-        psum += pv;
+        for (int q = 0; q < 32; ++q) {
+          float pv;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv) : "f"(fmaf(v[q], scale_log2e, -m_new)));
+          v[q] = pv;
+          s4[q & 3] += pv;
+        }
+        psum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const float pv = (k0 + cc * 32 + q < L) ? exp2f(fmaf(v[q], scale_log2e, -m_new)) : 0.f;
+          v[q] = pv;
+          psum += pv;
+        }
       }
 #pragma unroll
       for (int g8 = 0; g8 < 4; ++g8)

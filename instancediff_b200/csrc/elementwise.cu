@@ -127,47 +127,53 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ parti
 }
 
 // ---- GroupNorm finalize: partial sums -> per-(image,channel) affine (with time modulation) -------
-// grid = B, block = 512 threads.  The partial sums of image b are a [ntile][2G] matrix: thread t owns column
-// t % 2G and the rows t / 2G, t / 2G + 512 / 2G, ... (coalesced 8G-byte rows, four independent accumulators),
-// then the row lanes are folded through shared memory in a fixed order (deterministic, sharding-invariant).
-constexpr int kGnFinThreads = 512;
+// grid = (G, B), block = 256 threads: one CTA per (image, group).  Thread t adds the (sum, sum of squares) pairs of
+// rows t, t + 256, ... (four independent accumulators), the block folds them in a fixed order (deterministic,
+// sharding-invariant) and then writes the C/G channels of its group.  (One CTA per image took ~8 us per call at
+// 2048 partial rows: 34 calls per forward.)
+constexpr int kGnFinThreads = 256;
 __global__ void __launch_bounds__(kGnFinThreads)
 gn_finalize_kernel(const float* __restrict__ partial, int ntile, const float* __restrict__ gamma,
                    const float* __restrict__ beta, const float* __restrict__ t_scale,
                    const float* __restrict__ t_shift, int t_ld, float* __restrict__ scale_out,
                    float* __restrict__ shift_out, int C, int G, float inv_count, float eps) {
-  __shared__ float red[kGnFinThreads];
-  __shared__ float stat[32][2];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int ncol = 2 * G, col = tid % ncol, rl = tid / ncol, nrl = kGnFinThreads / ncol;
-  const float* src = partial + (size_t)b * ntile * ncol + col;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (rl < nrl) {
-    int t = rl;
-    for (; t + 3 * nrl < ntile; t += 4 * nrl) {
+  __shared__ float2 red[kGnFinThreads / 32];
+  __shared__ float stat[2];
+  const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const float2* src = reinterpret_cast<const float2*>(partial) + (size_t)b * ntile * G + g;
+  float2 acc[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  int t = tid;
+  for (; t + 3 * kGnFinThreads < ntile; t += 4 * kGnFinThreads) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) acc[u] += src[(size_t)(t + u * nrl) * ncol];
+    for (int u = 0; u < 4; ++u) {
+      const float2 v = __ldg(src + (size_t)(t + u * kGnFinThreads) * G);
+      acc[u].x += v.x;
+      acc[u].y += v.y;
     }
-    for (; t < ntile; t += nrl) acc[0] += src[(size_t)t * ncol];
   }
-  red[tid] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-  __syncthreads();
-  if (tid < ncol) {
-    float sum = 0.f;
-    for (int r = 0; r < nrl; ++r) sum += red[r * ncol + tid];
-    red[tid] = sum;                                   // [g][sum, sum of squares]; rows >= 1 are dead by now
+  for (; t < ntile; t += kGnFinThreads) {
+    const float2 v = __ldg(src + (size_t)t * G);
+    acc[0].x += v.x;
+    acc[0].y += v.y;
   }
+  float s1 = (acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), s2 = (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y);
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if ((tid & 31) == 0) red[tid >> 5] = make_float2(s1, s2);
   __syncthreads();
-  if (tid < G) {
-    const float mean = red[2 * tid] * inv_count;
-    const float var = fmaxf(red[2 * tid + 1] * inv_count - mean * mean, 0.f);
-    stat[tid][0] = mean;
-    stat[tid][1] = rsqrtf(var + eps);
+  if (tid == 0) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int w = 0; w < kGnFinThreads / 32; ++w) { a1 += red[w].x; a2 += red[w].y; }
+    const float mean = a1 * inv_count;
+    const float var = fmaxf(a2 * inv_count - mean * mean, 0.f);
+    stat[0] = mean;
+    stat[1] = rsqrtf(var + eps);
   }
   __syncthreads();
   const int cpg = C / G;
-  for (int c = tid; c < C; c += kGnFinThreads) {
-    const float mean = stat[c / cpg][0], rstd = stat[c / cpg][1];
+  const float mean = stat[0], rstd = stat[1];
+  for (int i = tid; i < cpg; i += kGnFinThreads) {
+    const int c = g * cpg + i;
     float sc = rstd * gamma[c];
     float sh = beta[c] - mean * sc;
     if (t_scale) {
@@ -321,7 +327,7 @@ int idiff_gn_finalize(const float* partial, int ntile, const float* gamma, const
   IDIFF_REQUIRE(partial && gamma && beta && scale_out && shift_out, "gn_finalize: null pointer");
   IDIFF_REQUIRE(B > 0 && ntile > 0 && G > 0 && G <= 32 && C % G == 0 && count_per_group > 0, "gn_finalize: bad sizes");
   IDIFF_REQUIRE((t_scale == nullptr) == (t_shift == nullptr), "gn_finalize: t_scale/t_shift must come together");
-  gn_finalize_kernel<<<B, kGnFinThreads, 0, as_stream(stream)>>>(partial, ntile, gamma, beta, t_scale, t_shift, t_ld,
+  gn_finalize_kernel<<<dim3((unsigned)G, (unsigned)B), kGnFinThreads, 0, as_stream(stream)>>>(partial, ntile, gamma, beta, t_scale, t_shift, t_ld,
                                                                  scale_out, shift_out, C, G,
                                                                  1.0f / (float)count_per_group, eps);
   return check_launch("gn_finalize");
