@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* emptyB = fullB + kMaxSB;
   uint64_t* tmem_full = emptyB + kMaxSB;           // [2]
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
-  uint64_t* wres_bar = tmem_empty + 2;             // resident weights landed
-  uint64_t* res_bar = wres_bar + 1;                // [8][2] residual tiles landed (per epilogue warp and staging set)
+  uint64_t* wres_bar = tmem_empty + 2;             // [16] resident weights landed (per 64-channel chunk)
+  uint64_t* res_bar = wres_bar + 16;               // [8][2] residual tiles landed (per epilogue warp and staging set)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     for (int i = 0; i < a.SA; ++i) { mbar_init(&fullA[i], kLoaderWarps); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < a.SB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps / 2); }
-    mbar_init(wres_bar, 1);
+    for (int i = 0; i < 16; ++i) mbar_init(&wres_bar[i], 1);
     for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     mbar_fence_init();
   }
@@ -750,12 +750,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const uint8_t* w0 = reinterpret_cast<const uint8_t*>(p.w);
     if (a.resident) {
       // every N tile's weights, once per CTA: [ntile][nk] stages of stageB bytes, contiguous in global memory
+      // One barrier per 64-channel chunk (single N tile, <= 16 chunks) so the first MMAs start as soon as the
+      // first chunk's taps have landed instead of after the whole burst -- matters for the small low-resolution
+      // layers, whose run time is a few microseconds; otherwise one barrier for everything.
       const uint32_t total = (uint32_t)a.ntiles_n * (uint32_t)nk * (uint32_t)stageB;
+      const bool per_chunk = a.ntiles_n == 1 && nchunks <= 16;
+      const uint32_t part = per_chunk ? (uint32_t)ntaps * (uint32_t)stageB : total;
       if (leader) {
-        mbar_arrive_expect_tx(wres_bar, total);
-        for (uint32_t off = 0; off < total; off += 32768) {
-          const uint32_t n = total - off < 32768u ? total - off : 32768u;
-          bulk_g2s(smem + a.offB + off, w0 + off, n, wres_bar);
+        uint32_t off = 0;
+        for (int ch = 0; off < total; ++ch) {
+          mbar_arrive_expect_tx(&wres_bar[ch], part);
+          for (uint32_t o2 = 0; o2 < part; o2 += 32768) {
+            const uint32_t n = part - o2 < 32768u ? part - o2 : 32768u;
+            bulk_g2s(smem + a.offB + off + o2, w0 + off + o2, n, &wres_bar[ch]);
+          }
+          off += part;
         }
       }
     } else {
@@ -785,8 +794,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const uint32_t a_hi = umma_desc_hi(G::SBO), b_hi = umma_desc_hi(sboB);
     const uint32_t a0 = smem_u32(smem + a.offA), b0 = smem_u32(smem + a.offB);
     long long pacc5 = 0, pacc6 = 0, pacc7 = 0, pacc8 = 0;
-    if (a.resident) {
-      mbar_wait(wres_bar, 0, 106);
+    const bool w_per_chunk = a.resident && a.ntiles_n == 1 && nchunks <= 16;
+    if (a.resident && !w_per_chunk) {
+      mbar_wait(&wres_bar[0], 0, 106);
       tc_fence_after();
     }
     // all indices below advance with compare-and-wrap only (uniform datapath; no modulo, no division)
@@ -808,6 +818,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       for (int ch = 0; ch < nchunks; ++ch) {
         tp = PROF_T();
         mbar_wait(&fullA[ra.slot], ra.phase, 104);
+        if (w_per_chunk && items_done == 0) mbar_wait(&wres_bar[ch], 0, 106);   // first item: this chunk's weights
         tc_fence_after();
         PROF_ADD(6, tp);
         // Tap loops stay ROLLED (one copy of the 4-MMA body): the tap's patch offset advances by one pixel per
