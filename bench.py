@@ -171,11 +171,23 @@ def run_cuda(args):
     from instancediff_b200 import ConditionalUNet, IRSDE, _lib
 
     rank, world, local = dist_env()
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on stdout when the first communicator is created; stdout must carry ONE
+        # JSON line, so fd 1 points at stderr while the communicator is set up.
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     B = BATCH_PER_GPU
     pk = peaks()
 

@@ -204,7 +204,8 @@ int idiff_linattn_context(const void* qkv, const float* w_out /*[C][128]*/, void
                           float* scratch, int B, int HW, int C, void* stream);
 size_t idiff_linattn_scratch_floats(int B, int HW);
 
-/* Fused linear attention block for C = 64 / 128 (q, k, v never touch HBM; three passes over x):
+/* Fused linear attention block for C = 64 / 128 (q, k, v never touch HBM; two passes over x, no k-max pre-pass:
+ * every chunk exponentiates against its own reference and the merge step rescales):
  *   out = x + LN_c(W_out (ctx^T q) + bias_out) * gain_out,  q = softmax_d(Wq x^) * qscale,
  *   ctx[h] = softmax_n(Wk x^)[h] (Wv x^)[h]^T / HW,  x^ = (x - mean) * rstd from row_stats [B*HW][2].
  * wq_packed / wk_packed: [128][C] weights with the pre-norm gain folded in, packed by pack_conv_weight(NT=128);

@@ -4,10 +4,11 @@
 //
 // The unfused chain (qkv GEMM -> k max -> context Gram -> merge -> output GEMM) moved 2176 B per pixel through HBM
 // (the 384-channel qkv tensor is written once and read twice).  Here q, k and v never exist in HBM: three passes
-// read x (128-256 B per pixel each) and only the result is written -- 4.2x less traffic at C = 64.
-//   pass 0  la_kmax : k^T = Wk x^^T per 128-pixel tile (tcgen05, M = 128 k-channels, N = 128 pixels): with the GEMM
-//                     transposed, a thread owns ONE k channel and the pixel maximum is a thread-local reduction.
-//   pass 1  la_ctx  : the same GEMM, e = exp(k - max) re-staged as a K-major A operand (K = pixels), then
+// read x (128-256 B per pixel each) and only the result is written.
+//   pass 1  la_ctx  : k^T = Wk x^^T per 128-pixel tile (tcgen05, M = 128 k-channels, N = 128 pixels): with the GEMM
+//                     transposed a thread owns ONE k channel, so softmax-over-pixels statistics are thread-local;
+//                     e = exp(k - ref) (ref = channel maximum of the chunk's first tile; softmax is invariant to the
+//                     constant, la_merge rescales the chunks) re-staged as a K-major A operand (K = pixels), then
 //                     S += e [x^ | 1]  (N = C + 16, x^ tile re-used as an MN-major B operand, accumulated in TMEM over
 //                     the CTA's whole chunk).  v is never formed:  ctx = (S Wv^T) / (rowsum HW)  is finished on
 //                     fp32 partial sums by la_merge, which also folds ctx into the per-image output weight
@@ -81,92 +82,11 @@ IDIFF_DEVINL void issue_mmas(uint32_t tacc, uint32_t a_lo, uint32_t a_hi, uint32
 }
 
 // =====================================================================================================
-// pass 0: per-(image, chunk) maxima of k over the chunk's pixels.  grid = (nchunk, B), block = 256.
-// =====================================================================================================
-template <int C>
-struct KmaxSmem {
-  static constexpr int X = 0, W = X + (C / 8) * LF_XP, RED = W + (C / 8) * LF_WP, BAR = RED + 128 * 4, TOTAL = BAR + 32;
-};
-
-template <int C>
-__global__ void __launch_bounds__(256, C == 64 ? 2 : 1)
-la_kmax_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats, const void* __restrict__ wk,
-               float* __restrict__ pmax, int HW) {
-  using S = KmaxSmem<C>;
-  extern __shared__ __align__(128) uint8_t sm[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + S::BAR);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-  float* red = reinterpret_cast<float*>(sm + S::RED);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int chunk = blockIdx.x, b = blockIdx.y, nchunk = gridDim.x;
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    mbar_fence_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 128);
-  copy_g2s(sm + S::W, wk, (C / 8) * LF_WP, tid);
-  const __nv_bfloat16* xb = x + (size_t)b * HW * C;
-  const float2* sb = stats + (size_t)b * HW;
-  const int r_begin = chunk * lf_chunk(HW), r_end = min(HW, r_begin + lf_chunk(HW));
-  XTile<C> xt;
-  xt.fetch(xb, sb, r_begin, tid);
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const bool leader = (warp == 0) && elect_one();
-  const uint32_t smem0 = smem_u32(sm);
-  const uint32_t idesc = umma_idesc_bf16(128, 128, 0);
-  const uint32_t w_lo = umma_desc_lo(smem0 + S::W, LF_WP), x_lo = umma_desc_lo(smem0 + S::X, LF_XP);
-  const uint32_t k_hi = umma_desc_hi(128);
-  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
-
-  float mx = -INFINITY;
-  int it = 0;
-  for (int r0 = r_begin; r0 < r_end; r0 += LF_PX, ++it) {
-    xt.store(sm + S::X, tid);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-      tc_fence_after();
-      if (leader) {
-        issue_mmas(tmem, w_lo, k_hi, (2 * LF_WP) >> 4, x_lo, k_hi, (2 * LF_XP) >> 4, idesc, C / 16, 0u);
-        umma_commit(bar);
-      }
-      __syncwarp();
-    }
-    if (r0 + LF_PX < r_end) xt.fetch(xb, sb, r0 + LF_PX, tid);    // next tile's loads fly during the MMA + epilogue
-    mbar_wait(bar, it & 1, 401);
-    tc_fence_after();
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      float v[32];
-      tmem_ld32(lane_addr + j * 32, v);
-      float m4[4] = {v[0], v[1], v[2], v[3]};
-#pragma unroll
-      for (int qq = 4; qq < 32; ++qq) m4[qq & 3] = fmaxf(m4[qq & 3], v[qq]);
-      mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
-    }
-    tc_fence_before();            // the barrier at the top of the next tile orders these reads before its MMA
-  }
-  // the two column halves of a row live in warps w and w + 4
-  __syncthreads();
-  if (warp >= 4) red[(warp & 3) * 32 + lane] = mx;
-  __syncthreads();
-  if (warp < 4) pmax[((size_t)b * nchunk + chunk) * 128 + warp * 32 + lane] = fmaxf(mx, red[warp * 32 + lane]);
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 128);
-  }
-}
-
-// =====================================================================================================
-// pass 1: S[d][c] = sum_n exp(k[d,n] - max[d]) x^[n,c], rowsum[d] = sum_n exp(..).  grid = (nchunk, B), block = 256.
-// part: [B][nchunk][128][C + 1] fp32 (column C = rowsum).
+// pass 1: S[d][c] = sum_n exp(k[d,n] - ref[d]) x^[n,c], rowsum[d] = sum_n exp(..).  grid = (nchunk, B), block = 256.
+// part: [B][nchunk][128][C + 1] fp32 (column C = rowsum);  pref: [B][nchunk][128] the chunk's reference.
+// softmax_n is invariant to the subtracted constant, so no exact-maximum pre-pass is needed: every chunk uses the
+// channel maximum of its FIRST tile as the reference (exponent clamped at +60 nats -- a later pixel would have to
+// exceed the reference by e^60 to matter) and la_merge rescales the chunk partials to the largest reference.
 // =====================================================================================================
 template <int C>
 struct CtxSmem {
@@ -179,7 +99,7 @@ struct CtxSmem {
 template <int C>
 __global__ void __launch_bounds__(256, C == 64 ? 2 : 1)
 la_ctx_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats, const void* __restrict__ wk,
-              const float* __restrict__ pmax, float* __restrict__ part, int HW) {
+              float* __restrict__ pref, float* __restrict__ part, int HW) {
   using S = CtxSmem<C>;
   extern __shared__ __align__(128) uint8_t sm[];
   uint64_t* bar1 = reinterpret_cast<uint64_t*>(sm + S::BAR);
@@ -195,11 +115,6 @@ la_ctx_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ st
   }
   if (warp == 0) tmem_alloc(tmem_slot, S::TMEM_COLS);
   copy_g2s(sm + S::W, wk, (C / 8) * LF_WP, tid);
-  if (tid < 128) {                                            // exact channel maximum over the whole image
-    float m = -INFINITY;
-    for (int c = 0; c < nchunk; ++c) m = fmaxf(m, pmax[((size_t)b * nchunk + c) * 128 + tid]);
-    kmax[tid] = m * LF_LOG2E;
-  }
   {                                                           // constant planes: ones (rowsum column), zeros
     const uint32_t one2 = 0x3F803F80u;                        // bf16(1.0) x2
     if (tid < 128) *reinterpret_cast<uint4*>(sm + S::X + (C / 8) * LF_XP + tid * 16) = make_uint4(one2, one2, one2, one2);
@@ -225,7 +140,7 @@ la_ctx_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ st
   const uint32_t k_hi = umma_desc_hi(128), xm_hi = umma_desc_hi(LF_XP);
   const int quarter = warp & 3, half = warp >> 2, d = quarter * 32 + lane;
   const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
-  const float mneg = -kmax[d];
+  float mneg = 0.f;                                            // -reference * log2(e), set on the first tile
 
   int it = 0;
   for (int r0 = r_begin; r0 < r_end; r0 += LF_PX, ++it) {
@@ -245,13 +160,36 @@ la_ctx_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ st
     if (r0 + LF_PX < r_end) xt.fetch(xb, sb, r0 + LF_PX, tid);
     mbar_wait(bar1, it & 1, 403);
     tc_fence_after();
-    // e = exp(k - max) for this thread's k channel and its 64 pixels -> K-major A tile [8-pixel group][d][8]
+    if (it == 0) {
+      // reference of this chunk = channel maximum over the first tile (two column halves live in warps w, w + 4)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float v[32];
+        tmem_ld32(lane_addr + j * 32, v);
+        float m4[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+        for (int qq = 4; qq < 32; ++qq) m4[qq & 3] = fmaxf(m4[qq & 3], v[qq]);
+        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+      }
+      if (half) kmax[d] = mx;
+      __syncthreads();
+      if (!half) {
+        mx = fmaxf(mx, kmax[d]);
+        pref[((size_t)b * nchunk + chunk) * 128 + d] = mx;
+      }
+      __syncthreads();
+      if (!half) kmax[d] = mx;
+      __syncthreads();
+      mneg = -kmax[d] * LF_LOG2E;
+    }
+    // e = exp(k - ref) for this thread's k channel and its 64 pixels -> K-major A tile [8-pixel group][d][8]
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       float v[32];
       tmem_ld32(lane_addr + j * 32, v);
 #pragma unroll
-      for (int qq = 0; qq < 32; ++qq) v[qq] = ex2_fast(fmaf(v[qq], LF_LOG2E, mneg));
+      for (int qq = 0; qq < 32; ++qq) v[qq] = ex2_fast(fminf(fmaf(v[qq], LF_LOG2E, mneg), 86.5f));
 #pragma unroll
       for (int g = 0; g < 4; ++g)
         *reinterpret_cast<uint4*>(sm + S::E + (half * 8 + j * 4 + g) * LF_TP + d * 16) = pack_bf16x8(v + g * 8);
@@ -299,22 +237,34 @@ la_ctx_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ st
 // =====================================================================================================
 template <int C>
 __global__ void __launch_bounds__(256)
-la_merge_kernel(const float* __restrict__ part, int nchunk, const float* __restrict__ wv, const float* __restrict__ w_out,
-                __nv_bfloat16* __restrict__ weff, int HW) {
+la_merge_kernel(const float* __restrict__ part, const float* __restrict__ pref, int nchunk, const float* __restrict__ wv,
+                const float* __restrict__ w_out, __nv_bfloat16* __restrict__ weff, int HW) {
   constexpr int R = 8;                                         // rows per CTA
+  constexpr int kMaxChunk = 512;
   __shared__ float Ssm[R * (C + 1)];
   __shared__ float ctx[R * 33];
+  __shared__ float fac[kMaxChunk * R];                         // exp(ref[chunk][d] - max_chunk ref[.][d])
   const int tid = threadIdx.x, h = blockIdx.x >> 2, d0 = (blockIdx.x & 3) * R, b = blockIdx.y;
+  const float* rf = pref + (size_t)b * nchunk * 128 + h * 32 + d0;
+  for (int i = tid; i < nchunk * R; i += 256) fac[i] = __ldg(rf + (size_t)(i >> 3) * 128 + (i & 7));
+  __syncthreads();
+  if (tid < R) {
+    float m = -INFINITY;
+    for (int c = 0; c < nchunk; ++c) m = fmaxf(m, fac[c * R + tid]);
+    for (int c = 0; c < nchunk; ++c) fac[c * R + tid] = __expf(fac[c * R + tid] - m);
+  }
+  __syncthreads();
   const float* p0 = part + ((size_t)b * nchunk * 128 + h * 32 + d0) * (C + 1);
   const size_t cstride = (size_t)128 * (C + 1);
   for (int i = tid; i < R * (C + 1); i += 256) {               // contiguous rows d0 .. d0+7 of every chunk
+    const int rr = i / (C + 1);
     float a4[4] = {0.f, 0.f, 0.f, 0.f};
     int c = 0;
     for (; c + 4 <= nchunk; c += 4) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) a4[u] += __ldg(p0 + (size_t)(c + u) * cstride + i);
+      for (int u = 0; u < 4; ++u) a4[u] = fmaf(__ldg(p0 + (size_t)(c + u) * cstride + i), fac[(c + u) * R + rr], a4[u]);
     }
-    for (; c < nchunk; ++c) a4[0] += __ldg(p0 + (size_t)c * cstride + i);
+    for (; c < nchunk; ++c) a4[0] = fmaf(__ldg(p0 + (size_t)c * cstride + i), fac[c * R + rr], a4[0]);
     Ssm[i] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
   }
   __syncthreads();
@@ -545,9 +495,7 @@ static int launch_fused(const void* x, const float* stats, const void* wq, const
                         int B, int HW, float qscale, float eps, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(la_kmax_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, KmaxSmem<C>::TOTAL);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(la_ctx_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtxSmem<C>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(la_ctx_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtxSmem<C>::TOTAL);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(la_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, OutSmem<C>::TOTAL);
     if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "linattn_fused attr: %s", cudaGetErrorString(e));
@@ -555,15 +503,14 @@ static int launch_fused(const void* x, const float* stats, const void* wq, const
   }
   const int nchunk = (HW + lf_chunk(HW) - 1) / lf_chunk(HW);
   float* part = scratch;
-  float* pmax = scratch + (size_t)B * nchunk * 128 * (C + 1);
+  float* pref = scratch + (size_t)B * nchunk * 128 * (C + 1);
   const dim3 grid((unsigned)nchunk, (unsigned)B);
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   const float2* sb = reinterpret_cast<const float2*>(stats);
-  la_kmax_kernel<C><<<grid, 256, KmaxSmem<C>::TOTAL, st>>>(xb, sb, wk, pmax, HW);
-  if (int rc = check_launch("la_kmax")) return rc;
-  la_ctx_kernel<C><<<grid, 256, CtxSmem<C>::TOTAL, st>>>(xb, sb, wk, pmax, part, HW);
+  la_ctx_kernel<C><<<grid, 256, CtxSmem<C>::TOTAL, st>>>(xb, sb, wk, pref, part, HW);
   if (int rc = check_launch("la_ctx")) return rc;
-  la_merge_kernel<C><<<dim3(16, (unsigned)B), 256, 0, st>>>(part, nchunk, wv, w_out, reinterpret_cast<__nv_bfloat16*>(weff), HW);
+  la_merge_kernel<C><<<dim3(16, (unsigned)B), 256, 0, st>>>(part, pref, nchunk, wv, w_out,
+                                                            reinterpret_cast<__nv_bfloat16*>(weff), HW);
   if (int rc = check_launch("la_merge")) return rc;
   la_out_kernel<C><<<grid, 256, OutSmem<C>::TOTAL, st>>>(xb, sb, wq, reinterpret_cast<const __nv_bfloat16*>(weff), bias, gain,
                                                          reinterpret_cast<__nv_bfloat16*>(out), HW, qscale, eps);
@@ -588,6 +535,7 @@ int idiff_linattn_fused(const void* x, const float* row_stats, const void* wq_pa
                     scratch && B > 0 && HW > 0, "linattn_fused: bad arguments");
   IDIFF_REQUIRE(C == 64 || C == 128, "linattn_fused: C must be 64 or 128 (got %d)", C);
   IDIFF_REQUIRE(HW % LF_PX == 0, "linattn_fused: H*W must be a multiple of %d", LF_PX);
+  IDIFF_REQUIRE((HW + lf_chunk(HW) - 1) / lf_chunk(HW) <= 512, "linattn_fused: more than 512 chunks per image");
   IDIFF_REQUIRE(aligned16(x) && aligned16(out) && aligned16(wq_packed) && aligned16(wk_packed) && aligned16(weff_scratch) &&
                     (reinterpret_cast<uintptr_t>(row_stats) & 7u) == 0, "linattn_fused: alignment");
   if (C == 64)

@@ -518,7 +518,7 @@ class _Plan:
         f = prefix + ".fn"
         to = pk[f + ".to_out"]
         if (f + ".fused") in pk and (H * W) % 128 == 0:
-            # q, k, v never touch HBM: k-max, context and output passes read x directly (csrc/linattn_fused.cu)
+            # q, k, v never touch HBM: the context and output passes read x directly (csrc/linattn_fused.cu)
             fu = pk[f + ".fused"]
             weff = self.tmp("la_weff", (B, Cc * 128))
             nfl = L.idiff_linattn_fused_scratch_floats(B, H * W, Cc)
@@ -528,10 +528,10 @@ class _Plan:
                     _ptr(to["bias"]), _ptr(to["g"]), _ptr(weff), _ptr(out.t), _ptr(scratch), B, H * W, Cc, 32 ** -0.5, 1e-5)
             self.ops.append(lambda s: check(L.idiff_linattn_fused(*args, s), "linattn_fused"))
             # algorithmic work: q and k projections, e * x^ context, q * Weff output
-            flops = 2.0 * B * H * W * (2 * 128 * Cc + 128 * (Cc + 16) + 128 * Cc)
+            flops = 2.0 * B * H * W * (2 * 128 * Cc + 128 * (Cc + 16) + 128 * Cc)     # k, q, e*x^, q*Weff
             self.op_info.append(("linattn_fused", flops, f"C{Cc} @{H}x{W}"))
-            self.op_bytes[len(self.ops) - 1] = 2.0 * B * H * W * Cc * 4 + 8.0 * B * H * W * 3   # 3 reads + 1 write + stats
-            self.n_launch += 4
+            self.op_bytes[len(self.ops) - 1] = 2.0 * B * H * W * Cc * 3 + 8.0 * B * H * W * 2   # 2 reads + 1 write + stats
+            self.n_launch += 3
             self.named[prefix] = out
             return out
         qkv = self.act(H, W, 384, tmp_name="la_qkv")

@@ -202,3 +202,41 @@ def test_linattn_fused_matches_reference(shape):
     assert rel_err(out, ref) <= 1e-2, describe(out, ref, "linattn fused")
     # the attention branch alone (without the dominating residual) must match as well
     assert rel_err(out.float() - xf, ref - xf) <= 3e-2, describe(out.float() - xf, ref - xf, "linattn branch")
+
+
+def test_linattn_fused_reference_far_below_the_maximum():
+    """The context pass exponentiates against the channel maximum of each chunk's FIRST tile (no k-max pre-pass).
+    Adversarial input: every pixel of the first tile is anti-aligned with the k weights and a late pixel is aligned,
+    so the true maximum exceeds the reference by ~40 nats; the rescaled merge must still reproduce softmax_n."""
+    from instancediff_b200 import ops
+    g = torch.Generator().manual_seed(23)
+    B, H, W, Cc = 1, 32, 32, 64
+    wqkv = ((torch.rand(384, Cc, generator=g) * 2 - 1) * (2.0 / Cc ** 0.5)).cuda()
+    wqkv[128:256] *= 2.5                                               # large k logits
+    wdir = wqkv[128:256].mean(0)                                       # a direction most k channels like
+    wdir = wdir - wdir.mean()
+    wdir = wdir / wdir.norm() * Cc ** 0.5
+    x = rand_act(B, H, W, Cc, g).float() * 0.05
+    x.reshape(-1, Cc)[:128] -= wdir                                    # first tile: anti-aligned
+    x.reshape(-1, Cc)[700] += 4 * wdir                                 # one late pixel: strongly aligned
+    x = x.to(torch.bfloat16)
+    xf = x.float()
+    mean, var = xf.mean(-1, keepdim=True), xf.var(-1, unbiased=False, keepdim=True)
+    rstd = torch.rsqrt(var + 1e-5)
+    stats = torch.cat([mean, rstd], -1).reshape(-1, 2).contiguous()
+    ones, zeros = torch.ones(Cc).cuda(), torch.zeros(Cc).cuda()
+    w_out = ((torch.rand(Cc, 128, generator=g) * 2 - 1) / 128 ** 0.5).cuda()
+    out = ops.linattn_fused(x, stats, wqkv, ones, w_out, zeros, ones)
+    torch.cuda.synchronize()
+    xn = ((xf - mean) * rstd).to(torch.bfloat16).float()               # the operand the kernel sees
+    qkv = xn.reshape(B, H * W, Cc) @ wqkv.to(torch.bfloat16).float().t()
+    q, k, v = (t.reshape(B, H * W, 4, 32).permute(0, 2, 3, 1) for t in qkv.chunk(3, dim=-1))
+    assert (k.amax(-1) - k[..., :128].amax(-1)).max() > 20             # the reference really is far below the max
+    ctx = torch.einsum("bhdn,bhen->bhde", k.softmax(dim=-1), v / (H * W))
+    o = torch.einsum("bhde,bhdn->bhen", ctx, q.softmax(dim=-2) * 32 ** -0.5).reshape(B, 128, H * W).permute(0, 2, 1)
+    y = o @ w_out.t()
+    y = (y - y.mean(-1, keepdim=True)) * torch.rsqrt(y.var(-1, unbiased=False, keepdim=True) + 1e-5)
+    ref = xf + y.reshape(B, H, W, Cc)
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref) <= 1e-2, describe(out, ref, "linattn fused, adversarial reference")
+    assert rel_err(out.float() - xf, ref - xf) <= 5e-2, describe(out.float() - xf, ref - xf, "branch")
