@@ -225,7 +225,7 @@ def test_linattn_fused_reference_far_below_the_maximum():
     rstd = torch.rsqrt(var + 1e-5)
     stats = torch.cat([mean, rstd], -1).reshape(-1, 2).contiguous()
     ones, zeros = torch.ones(Cc).cuda(), torch.zeros(Cc).cuda()
-    w_out = ((torch.rand(Cc, 128, generator=g) * 2 - 1) / 128 ** 0.5).cuda()
+    w_out = ((torch.rand(Cc, 128, generator=g) * 2 - 1) * 300.0).cuda()   # large: the channel LayerNorm sees var >> eps
     out = ops.linattn_fused(x, stats, wqkv, ones, w_out, zeros, ones)
     torch.cuda.synchronize()
     xn = ((xf - mean) * rstd).to(torch.bfloat16).float()               # the operand the kernel sees
@@ -235,8 +235,14 @@ def test_linattn_fused_reference_far_below_the_maximum():
     ctx = torch.einsum("bhdn,bhen->bhde", k.softmax(dim=-1), v / (H * W))
     o = torch.einsum("bhde,bhdn->bhen", ctx, q.softmax(dim=-2) * 32 ** -0.5).reshape(B, 128, H * W).permute(0, 2, 1)
     y = o @ w_out.t()
+    assert y.var(-1, unbiased=False).median() > 1e-3
     y = (y - y.mean(-1, keepdim=True)) * torch.rsqrt(y.var(-1, unbiased=False, keepdim=True) + 1e-5)
     ref = xf + y.reshape(B, H, W, Cc)
     assert torch.isfinite(out).all()
     assert rel_err(out, ref) <= 1e-2, describe(out, ref, "linattn fused, adversarial reference")
-    assert rel_err(out.float() - xf, ref - xf) <= 5e-2, describe(out.float() - xf, ref - xf, "branch")
+    # the attention branch alone on the undoctored pixels (|x| ~ 0.05 there, so the bf16 rounding of x + branch does
+    # not mask it): rows 0-3 hold the anti-aligned tile, row 21 the aligned pixel
+    keep = [r for r in range(H) if r >= 4 and r != 700 // W]
+    br, br_ref = (out.float() - xf)[:, keep], (ref - xf)[:, keep]
+    assert br_ref.abs().max() > 0.5
+    assert rel_err(br, br_ref) <= 3e-2, describe(br, br_ref, "branch on undoctored rows")
