@@ -58,20 +58,35 @@ stem_tc_kernel(const float* __restrict__ x, const float* __restrict__ mu, const 
   const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
   uint32_t phase = 0;
 
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+  // patch loader split into a register fetch and a shared-memory store: the NEXT tile's 22x14 patch is in flight
+  // while the current tile is gathered, multiplied and stored (the serialised version exposed one global-load
+  // latency per tile)
+  constexpr int NPF = (STM_PH * STM_PW + 127) / 128;            // 3 patch pixels per thread
+  float2 pf[NPF];
+  auto fetch_patch = [&](int tile) {
     const int tx = tile % tiles_x, r = tile / tiles_x, ty = r % tiles_y, b = r / tiles_y;
     const int oy0 = ty * STM_TH, ox0 = tx * STM_TW;
     const float* xb = x + (size_t)b * H * W;
     const float* mb = mu + (size_t)b * H * W;
-    for (int i = tid; i < STM_PH * STM_PW; i += 128) {
+#pragma unroll
+    for (int k = 0; k < NPF; ++k) {
+      const int i = tid + 128 * k;
       const int py = i / STM_PW, px = i - py * STM_PW, iy = oy0 + py - 3, ix = ox0 + px - 3;
       float2 v = make_float2(0.f, 0.f);
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      if (i < STM_PH * STM_PW && iy >= 0 && iy < H && ix >= 0 && ix < W) {
         v.y = __ldg(mb + (size_t)iy * W + ix);
         v.x = __ldg(xb + (size_t)iy * W + ix) - v.y;             // channel 0 = x - mu, channel 1 = mu
       }
-      patch[i] = v;
+      pf[k] = v;
     }
+  };
+  if ((int)blockIdx.x < total) fetch_patch(blockIdx.x);
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int tx = tile % tiles_x, r = tile / tiles_x, ty = r % tiles_y, b = r / tiles_y;
+    const int oy0 = ty * STM_TH, ox0 = tx * STM_TW;
+#pragma unroll
+    for (int k = 0; k < NPF; ++k)
+      if (tid + 128 * k < STM_PH * STM_PW) patch[tid + 128 * k] = pf[k];
     __syncthreads();
     // in-kernel im2col: this thread's pixel row, 13 groups of 4 taps x 2 channels, as bf16 hi and lo parts
     const float2* pp = patch + ti * STM_PW + tj;
@@ -111,6 +126,7 @@ stem_tc_kernel(const float* __restrict__ x, const float* __restrict__ mu, const 
       }
       __syncwarp();
     }
+    if (tile + (int)gridDim.x < total) fetch_patch(tile + gridDim.x);
     mbar_wait(bar, phase, 301);
     phase ^= 1u;
     tc_fence_after();

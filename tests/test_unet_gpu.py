@@ -214,3 +214,24 @@ def test_full_size_invariants_256(nets):
     assert torch.equal(a, d2), f"2 shards vs 1: {(a - d2).abs().max():.3e}"
     # the update moved x by a bounded amount per step (|a_t|, |b_t|, |c_t| <= 0.18 at t >= 98)
     assert (a - mu).abs().max().item() < 6.0
+
+
+def test_testum_style_driver_end_to_end(tmp_path):
+    """tools/test_um.py: `.raw` data set -> reverse SDE at the data set's native 224x224 -> metrics + triptych files
+    (testUM.py:43-175 sequence).  Checks the plumbing; numerical parity of the sampler is covered above."""
+    import importlib.util
+    import os
+    import numpy as np
+    from oracle.gen_golden_io import NAMES, make_inputs
+    spec = importlib.util.spec_from_file_location("test_um", os.path.join(os.path.dirname(__file__), "..", "tools", "test_um.py"))
+    drv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(drv)
+    flist = make_inputs(str(tmp_path / "in"))if (tmp_path / "in").mkdir() is None else None
+    res = drv.run(flist, str(tmp_path / "out"), NAMES[:2], max_items=2, T=4)
+    assert sum(r["num"] for r in res.values()) == 2
+    for name, r in res.items():
+        assert all(np.isfinite(r["RMSE"])) and all(np.isfinite(r["PSNR"]))
+        files = os.listdir(tmp_path / "out" / name)
+        assert len(files) == r["num"] and all(f.endswith("_672x224x1.raw") for f in files)
+        trip = np.fromfile(str(tmp_path / "out" / name / files[0]), dtype=np.float32)
+        assert trip.size == 224 * 672 and np.isfinite(trip).all()
