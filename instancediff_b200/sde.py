@@ -312,6 +312,8 @@ class IRSDE(SDE):
         """The hot loop (:244-261): T sequential (model forward, fused update) pairs, no host sync inside."""
         T = self.sample_T if T < 0 else T
         xt = _require_cuda_f32("xt", xt)
+        if T == 0 or xt.numel() == 0:                  # empty loop / empty batch: the reference returns the clone (:247)
+            return xt.clone()
         if self._graph_eligible(xt, save_states, kwargs):
             return self._reverse_sde_graph(xt, T, kwargs)
         x = xt.clone()

@@ -367,6 +367,8 @@ class ConditionalUNet:
 
     def forward(self, xt, cond, time, *unused, image_context=None, **unused_kw):
         H, W = xt.shape[-2:]
+        if xt.shape[0] == 0:                           # empty batch: nothing to launch
+            return torch.empty_like(xt)
         ph, pw = (-H) % 16, (-W) % 16
         if ph or pw:                                 # reflect-pad right/bottom, crop after (App. A)
             xt = torch.nn.functional.pad(xt, (0, pw, 0, ph), mode="reflect")

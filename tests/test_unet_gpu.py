@@ -235,3 +235,23 @@ def test_testum_style_driver_end_to_end(tmp_path):
         assert len(files) == r["num"] and all(f.endswith("_672x224x1.raw") for f in files)
         trip = np.fromfile(str(tmp_path / "out" / name / files[0]), dtype=np.float32)
         assert trip.size == 224 * 672 and np.isfinite(trip).all()
+
+
+def test_empty_batch_and_zero_steps(nets):
+    """Edge cases of the loop (utils/sde_utils.py:244-261): T = 0 returns a clone of the input, an empty batch returns
+    an empty tensor -- in both the eager and the CUDA-graph configuration, without launching anything."""
+    from instancediff_b200 import IRSDE
+    _, net = nets
+    x, mu, ctx = _inputs(2, 32, 32, seed=4)
+    for graph in (False, True):
+        sde = IRSDE(0.4, T=100, schedule="cosine", eps=0.01, device=torch.device("cuda"))
+        sde.set_model(net)
+        sde.set_mu(mu)
+        sde.noise_source = "philox"
+        sde.use_cuda_graph = graph
+        out = sde.reverse_sde(x, T=0, image_context=ctx)
+        assert torch.equal(out, x) and out.data_ptr() != x.data_ptr()
+        sde.set_mu(mu[:0])
+        e = sde.reverse_sde(x[:0], T=5, image_context=ctx[:0])
+        assert tuple(e.shape) == (0, 1, 32, 32)
+    assert tuple(net(x[:0], mu[:0], 3.0, image_context=ctx[:0]).shape) == (0, 1, 32, 32)
