@@ -40,6 +40,26 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
+def conv_traffic_from_profile(n_launches):
+    """Mean DRAM bytes per conv_gemm launch (read + write) of one forward, from the committed ncu capture; None when
+    the file is missing or was taken with a different launch count."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01s2_final_conv_gemm_dram_bytes_ncu.csv")
+    if not os.path.exists(path):
+        return None
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    h = rows[0]
+    ii, mi, vi = h.index("ID"), h.index("Metric Name"), h.index("Metric Value")
+    ids, total = set(), 0.0
+    for r in rows[1:]:
+        if r[mi].startswith("dram__bytes"):
+            ids.add(r[ii])
+            total += float(r[vi].replace(",", ""))
+    if len(ids) != n_launches:
+        return None
+    return total / len(ids)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -305,6 +325,10 @@ def run_cuda(args):
     sde_big_gbs = 16.0 * n_big / (sde_big_us * 1e-6) / 1e9
     del xb, eb, mb
 
+    # DRAM bytes of the conv_gemm launches of one forward from the committed ncu capture of this configuration
+    # (profiles/r01s2_final_conv_gemm_dram_bytes_ncu.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch)
+    conv_traffic = conv_traffic_from_profile(conv["n"]) if B == 32 and RES == 256 else None
+    conv_algo_bytes = sum(nb for kind, _, _, _, nb in rows if kind == "conv_gemm")
     launches_per_fwd = plan.n_launch
     gpu_launches = args.steps * (T_STEPS * (launches_per_fwd + 2) + 0)
 
@@ -325,7 +349,8 @@ def run_cuda(args):
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all conv/linear layers)",
                      "achieved": conv_tflops, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                      "frac": conv_tflops / pk["tf_sustained"], "frac_of_burst": conv_tflops / pk["tf_burst"],
-                     "traffic": None, "launches_per_forward": conv["n"], "ms_per_forward": conv["ms"],
+                     "traffic": conv_traffic, "algorithmic_bytes_per_launch": conv_algo_bytes / conv["n"],
+                     "launches_per_forward": conv["n"], "ms_per_forward": conv["ms"],
                      "share_of_forward": conv["ms"] / fwd_ms,
                      "note": "achieved = sum of algorithmic 2*M*N*K over the conv_gemm launches of one forward / sum of their "
                              "CUDA-event durations; peak = MEASURED_PEAKS bf16 sustained (kernel timed inside a long step)"},
