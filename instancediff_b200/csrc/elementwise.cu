@@ -92,6 +92,64 @@ rowwise_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restr
   }
 }
 
+// ---- ResBlock tail, streaming version (no row statistics): out = silu(y*scale+shift) + res -------------------
+// The grid stride is a multiple of the vectors per row, so a thread keeps ONE 8-channel group for its whole life:
+// the per-(image, channel) affine is re-read only when the image changes, indices are 32-bit shifts (the generic
+// kernel above spends ~100 instructions per vector on 64-bit divisions and four parameter loads), and two vectors
+// are in flight per thread.  rows * C / 8 must fit in 32 bits.
+template <int LSH, bool STATS>   // log2(C / 8); STATS: also write the per-row LayerNorm (mean, rstd) of the result
+__global__ void __launch_bounds__(256)
+block_tail_stream_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res, const float* __restrict__ scale,
+                         const float* __restrict__ shift, uint4* __restrict__ out, float2* __restrict__ row_stats,
+                         float eps, uint32_t nvec, uint32_t HW) {
+  constexpr int C = 8 << LSH;
+  const uint32_t stride = gridDim.x * 256u;
+  const int c0 = (int)(threadIdx.x & ((1u << LSH) - 1u)) * 8;
+  float sc[8], sh[8];
+  uint32_t cur_img = 0xFFFFFFFFu;
+  auto params = [&](uint32_t img) {
+    if (img == cur_img) return;
+    cur_img = img;
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + (size_t)img * C + c0));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + (size_t)img * C + c0 + 4));
+    const float4 t0 = __ldg(reinterpret_cast<const float4*>(shift + (size_t)img * C + c0));
+    const float4 t1 = __ldg(reinterpret_cast<const float4*>(shift + (size_t)img * C + c0 + 4));
+    sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+    sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
+  };
+  auto finish = [&](uint32_t i, const uint4& qy, const uint4& qr) {
+    params((i >> LSH) / HW);
+    float f[8], r[8];
+    unpack_bf16x8(qy, f);
+    unpack_bf16x8(qr, r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = silu_fast(fmaf(f[e], sc[e], sh[e])) + r[e];
+    __stcs(out + i, pack_bf16x8(f));
+    if (STATS) {                                              // the C/8 lanes of a row are adjacent lanes of one warp
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s1 += f[e]; s2 = fmaf(f[e], f[e], s2); }
+#pragma unroll
+      for (int o = 1; o < (1 << LSH); o <<= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (c0 == 0) {
+        const float mean = s1 * (1.f / C), var = fmaxf(s2 * (1.f / C) - mean * mean, 0.f);
+        row_stats[i >> LSH] = make_float2(mean, rsqrtf(var + eps));
+      }
+    }
+  };
+  uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  for (; i + stride < nvec; i += 2 * stride) {
+    const uint4 y0 = __ldcs(y + i), y1 = __ldcs(y + i + stride);
+    const uint4 r0 = __ldcs(res + i), r1 = __ldcs(res + i + stride);
+    finish(i, y0, r0);
+    finish(i + stride, y1, r1);
+  }
+  if (i < nvec) finish(i, __ldcs(y + i), __ldcs(res + i));
+}
+
 // ---- GroupNorm statistics of a bf16 [B][HW][C] tensor -> partial[(b*ntile+tile)*G+g][2] -----------
 constexpr int GN_TILE_ROWS = 128;
 __global__ void __launch_bounds__(256)
@@ -286,6 +344,30 @@ int idiff_block_tail(const void* y, const float* scale, const float* shift, cons
   IDIFF_REQUIRE(y && scale && shift && out && B > 0 && HW > 0, "block_tail: bad arguments");
   if (int rc = check_c(C, "block_tail")) return rc;
   const size_t rows = (size_t)B * HW;
+  // streaming kernel: needs a residual, 32-bit vector indices and whole warps (the row-statistics shuffles assume
+  // converged warps: nvec % 32 == 0 holds for every H*W that is a multiple of 4)
+  if (res && rows * (size_t)(C / 8) < 0xFFFFFFFFull && (rows * (size_t)(C / 8)) % 32 == 0 && aligned16(y) && aligned16(res) &&
+      aligned16(out)) {
+    const uint32_t nvec = (uint32_t)(rows * (size_t)(C / 8));
+    unsigned blocks = (nvec + 511u) / 512u;                   // two vectors per thread
+    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    if (blocks < 1u) blocks = 1u;
+    const uint4 *yp = (const uint4*)y, *rp = (const uint4*)res;
+    uint4* op = (uint4*)out;
+    float2* sp = reinterpret_cast<float2*>(out_row_stats);
+    cudaStream_t st = as_stream(stream);
+    const uint32_t hw = (uint32_t)HW;
+#define IDIFF_TAIL(LSH)                                                                                              \
+    do {                                                                                                               \
+      if (sp) block_tail_stream_kernel<LSH, true><<<blocks, 256, 0, st>>>(yp, rp, scale, shift, op, sp, ln_eps, nvec, hw); \
+      else block_tail_stream_kernel<LSH, false><<<blocks, 256, 0, st>>>(yp, rp, scale, shift, op, sp, ln_eps, nvec, hw);  \
+    } while (0)
+    if (C == 64) IDIFF_TAIL(3);
+    else if (C == 128) IDIFF_TAIL(4);
+    else IDIFF_TAIL(5);
+#undef IDIFF_TAIL
+    return check_launch("block_tail");
+  }
   rowwise_kernel<0><<<blocks_for(rows * (C / 8), 256), 256, 0, as_stream(stream)>>>(
       (const __nv_bfloat16*)y, (const __nv_bfloat16*)res, scale, shift, nullptr, (__nv_bfloat16*)out, out_row_stats,
       ln_eps, rows, HW, C);
