@@ -8,7 +8,8 @@
 //   as a bf16 hi/lo pair), padded to 112; the block is stored TWICE: bf16(a) and bf16(a - bf16(a)), so the
 //   activations keep ~16 mantissa bits (x_t feeds the SDE recursion directly) while the weights are bf16 like every
 //   other layer.  Weights are pre-packed on the host into the shared-memory image (packing.py::pack_stem_weight).
-// Persistent CTAs (2 per SM: gather of one overlaps MMA / epilogue of the other), 128 threads = 128 accumulator rows.
+// Persistent CTAs (2 per SM: gather of one overlaps MMA / epilogue of the other), 256 threads: two threads per
+// accumulator row split the im2col groups and the output columns.
 // Spec: SURVEY.md App. A (init_conv); serves `self.model(x, self.mu, t*scale)`, utils/sde_utils.py:198.
 #include "common.cuh"
 #include "host_common.h"
@@ -17,18 +18,49 @@ namespace idiff {
 
 constexpr int STM_TH = 16, STM_TW = 8;
 constexpr int STM_PH = STM_TH + 6, STM_PW = STM_TW + 6;     // 22 x 14 patch
+constexpr int STM_PP = 24;                                  // patch row pitch in shared memory (float2 units):
+                                                            // == 8 mod 16, so the 8-byte gathers of a half warp
+                                                            // (2 tile rows x 8 pixels) hit 32 distinct banks
 constexpr int STM_GH = 14;                                  // 8-wide K groups per half (hi / lo): 112 values
 constexpr int STM_G = 2 * STM_GH;                           // 28 groups, K = 224 = 14 MMAs of K = 16
 constexpr int STM_LBO_A = 128 * 16;                         // one K group of A: 128 rows x 16 B
 constexpr int STM_LBO_B = 64 * 16;                          // one K group of B: 64 rows x 16 B
 constexpr int STM_OFF_B = STM_G * STM_LBO_A;                // 57344
 constexpr int STM_OFF_P = STM_OFF_B + STM_G * STM_LBO_B;    // 86016
-constexpr int STM_OFF_BAR = STM_OFF_P + STM_PH * STM_PW * 8;
+constexpr int STM_OFF_BAR = STM_OFF_P + STM_PH * STM_PP * 8;
 constexpr int STM_SMEM = STM_OFF_BAR + 16;
 
 int watchdog_stem(int clear) { return watchdog_read_tu(clear); }
 
-__global__ void __launch_bounds__(128)
+// im2col groups G0 .. G0+NG-1 of one pixel row: 4 taps x 2 channels each, stored as bf16 hi and lo parts.  All tap
+// offsets are compile-time constants.
+template <int G0, int NG>
+IDIFF_DEVINL void stem_gather(const float2* __restrict__ pp, uint8_t* sA, int row) {
+#pragma unroll
+  for (int g = G0; g < G0 + NG; ++g) {
+    float v[8];
+#pragma unroll
+    for (int t4 = 0; t4 < 4; ++t4) {
+      const int tap = 4 * g + t4;
+      if (tap < 49) {
+        const float2 pv = pp[(tap / 7) * STM_PP + (tap % 7)];
+        v[2 * t4] = pv.x;
+        v[2 * t4 + 1] = pv.y;
+      } else {
+        v[2 * t4] = v[2 * t4 + 1] = tap == 49 ? 1.f : 0.f;     // k' = 98, 99: the bias rows of the weights
+      }
+    }
+    const uint4 hi = pack_bf16x8(v);
+    float h[8];
+    unpack_bf16x8(hi, h);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] -= h[e];
+    *reinterpret_cast<uint4*>(sA + g * STM_LBO_A + row * 16) = hi;
+    *reinterpret_cast<uint4*>(sA + (STM_GH + g) * STM_LBO_A + row * 16) = pack_bf16x8(v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
 stem_tc_kernel(const float* __restrict__ x, const float* __restrict__ mu, const uint4* __restrict__ wpk,
                __nv_bfloat16* __restrict__ out, int H, int W, int tiles_x, int tiles_y, int total) {
   extern __shared__ __align__(128) uint8_t sm[];
@@ -38,17 +70,17 @@ stem_tc_kernel(const float* __restrict__ x, const float* __restrict__ mu, const 
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + STM_OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int ti = tid >> 3, tj = tid & 7;
+  const int row = tid & 127, part = tid >> 7;                  // accumulator row (tile pixel) / which half of the work
+  const int ti = row >> 3, tj = row & 7;
 
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 64);
-  for (int i = tid; i < STM_G * STM_LBO_B / 16; i += 128) reinterpret_cast<uint4*>(sB)[i] = __ldg(wpk + i);
+  for (int i = tid; i < STM_G * STM_LBO_B / 16; i += 256) reinterpret_cast<uint4*>(sB)[i] = __ldg(wpk + i);
   // the all-zero tail group of each half is written once
-  *reinterpret_cast<uint4*>(sA + (STM_GH - 1) * STM_LBO_A + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
-  *reinterpret_cast<uint4*>(sA + (STM_G - 1) * STM_LBO_A + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(sA + (part ? STM_G - 1 : STM_GH - 1) * STM_LBO_A + row * 16) = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -61,7 +93,7 @@ stem_tc_kernel(const float* __restrict__ x, const float* __restrict__ mu, const 
   // patch loader split into a register fetch and a shared-memory store: the NEXT tile's 22x14 patch is in flight
   // while the current tile is gathered, multiplied and stored (the serialised version exposed one global-load
   // latency per tile)
-  constexpr int NPF = (STM_PH * STM_PW + 127) / 128;            // 3 patch pixels per thread
+  constexpr int NPF = (STM_PH * STM_PW + 255) / 256;            // 2 patch pixels per thread
   float2 pf[NPF];
   auto fetch_patch = [&](int tile) {
     const int tx = tile % tiles_x, r = tile / tiles_x, ty = r % tiles_y, b = r / tiles_y;
@@ -70,7 +102,7 @@ stem_tc_kernel(const float* __restrict__ x, const float* __restrict__ mu, const 
     const float* mb = mu + (size_t)b * H * W;
 #pragma unroll
     for (int k = 0; k < NPF; ++k) {
-      const int i = tid + 128 * k;
+      const int i = tid + 256 * k;
       const int py = i / STM_PW, px = i - py * STM_PW, iy = oy0 + py - 3, ix = ox0 + px - 3;
       float2 v = make_float2(0.f, 0.f);
       if (i < STM_PH * STM_PW && iy >= 0 && iy < H && ix >= 0 && ix < W) {
@@ -86,32 +118,16 @@ stem_tc_kernel(const float* __restrict__ x, const float* __restrict__ mu, const 
     const int oy0 = ty * STM_TH, ox0 = tx * STM_TW;
 #pragma unroll
     for (int k = 0; k < NPF; ++k)
-      if (tid + 128 * k < STM_PH * STM_PW) patch[tid + 128 * k] = pf[k];
-    __syncthreads();
-    // in-kernel im2col: this thread's pixel row, 13 groups of 4 taps x 2 channels, as bf16 hi and lo parts
-    const float2* pp = patch + ti * STM_PW + tj;
-#pragma unroll
-    for (int g = 0; g < STM_GH - 1; ++g) {
-      float v[8];
-#pragma unroll
-      for (int t4 = 0; t4 < 4; ++t4) {
-        const int tap = 4 * g + t4;
-        if (tap < 49) {
-          const float2 pv = pp[(tap / 7) * STM_PW + (tap % 7)];
-          v[2 * t4] = pv.x;
-          v[2 * t4 + 1] = pv.y;
-        } else {
-          v[2 * t4] = v[2 * t4 + 1] = tap == 49 ? 1.f : 0.f;     // k' = 98, 99: the bias rows of the weights
-        }
+      if (tid + 256 * k < STM_PH * STM_PW) {
+        const int i = tid + 256 * k, py = i / STM_PW;
+        patch[py * STM_PP + (i - py * STM_PW)] = pf[k];
       }
-      const uint4 hi = pack_bf16x8(v);
-      float h[8];
-      unpack_bf16x8(hi, h);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] -= h[e];
-      *reinterpret_cast<uint4*>(sA + g * STM_LBO_A + tid * 16) = hi;
-      *reinterpret_cast<uint4*>(sA + (STM_GH + g) * STM_LBO_A + tid * 16) = pack_bf16x8(v);
-    }
+    __syncthreads();
+    // in-kernel im2col: this thread's pixel row, its 7 (part 0) or 6 (part 1) of the 13 groups of 4 taps x 2
+    // channels, as bf16 hi and lo parts
+    const float2* pp = patch + ti * STM_PP + tj;
+    if (part == 0) stem_gather<0, 7>(pp, sA, row);
+    else stem_gather<7, 6>(pp, sA, row);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -133,13 +149,12 @@ stem_tc_kernel(const float* __restrict__ x, const float* __restrict__ mu, const 
     const int oy = oy0 + ti, ox = ox0 + tj;
     const bool valid = oy < H && ox < W;
     uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)b * H + (valid ? oy : 0)) * W + (valid ? ox : 0)) * 64);
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float v[32];
-      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(half * 32), v);
+    {
+      float v[32];                                             // warps 0-3: columns 0..31, warps 4-7: columns 32..63
+      tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(part * 32), v);
       if (valid) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dst[half * 4 + q] = pack_bf16x8(v + 8 * q);
+        for (int q = 0; q < 4; ++q) dst[part * 4 + q] = pack_bf16x8(v + 8 * q);
       }
     }
     tc_fence_before();       // the next tile's barriers order these TMEM reads before its first MMA
@@ -175,7 +190,7 @@ int idiff_stem_conv7_tc(const float* x, const float* mu, const void* w_packed, v
   const int tiles_x = (W + STM_TW - 1) / STM_TW, tiles_y = (H + STM_TH - 1) / STM_TH;
   const int total = tiles_x * tiles_y * B;
   const int grid = total < 2 * num_sms ? total : 2 * num_sms;
-  stem_tc_kernel<<<grid, 128, STM_SMEM, as_stream(stream)>>>(x, mu, (const uint4*)w_packed, (__nv_bfloat16*)out, H, W,
+  stem_tc_kernel<<<grid, 256, STM_SMEM, as_stream(stream)>>>(x, mu, (const uint4*)w_packed, (__nv_bfloat16*)out, H, W,
                                                              tiles_x, tiles_y, total);
   return check_launch("stem_conv7_tc");
 }
