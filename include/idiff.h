@@ -162,8 +162,10 @@ int idiff_stem_conv7_tc(const float* x, const float* mu, const void* w_packed, v
                         void* stream);
 int idiff_stem_packed_bytes(void);
 
-/* Head: 3x3 conv C -> 1 channel, fp32 out [B,1,H,W].  w: fp32 [3][3][C]. */
-int idiff_head_conv3(const void* src, const float* w, float bias, float* out, int B, int H, int W, int C,
+/* Head: 3x3 conv C = 64 -> 1 channel, fp32 out [B,1,H,W], on warp-level tensor-core MMAs (mma.sync m16n8k16).
+ * w: the B fragments packed by instancediff_b200/packing.py::pack_head_weight (bf16 hi + lo parts of the fp32
+ * weights in MMA columns 0 / 1, 9216 bytes). */
+int idiff_head_conv3(const void* src, const void* w, float bias, float* out, int B, int H, int W, int C,
                      void* stream);
 
 /* Sinusoidal embedding -> Linear -> GELU -> Linear, then every ResBlock's Linear(SiLU(temb)).

@@ -1,7 +1,7 @@
-// CUDA-core convolutions for the two shapes that are not tensor-core shaped, plus a plain reference
-// convolution used only by the tests to validate the tcgen05 engine.
-//   stem : cat([x - mu, mu]) -> 7x7, 2 -> nf channels   (K = 98, 0.4 % of the FLOPs, HBM/LSU bound)
-//   head : 3x3, nf -> 1 channel                          (9 FLOP/B, HBM bound)
+// The two convolutions that are not shaped for the tcgen05 engine, plus a plain reference convolution used only by
+// the tests to validate the engine.
+//   stem : cat([x - mu, mu]) -> 7x7, 2 -> nf channels, CUDA cores, fp32: the VALIDATION reference of stem_tc.cu
+//   head : 3x3, nf -> 1 channel, warp-level tensor-core MMAs (mma.sync), HBM bound
 // Spec: SURVEY.md App. A; serves `self.model(x, self.mu, t*scale)`, utils/sde_utils.py:198.
 #include "common.cuh"
 #include "host_common.h"
@@ -62,46 +62,80 @@ stem_conv7_kernel(const float* __restrict__ x, const float* __restrict__ mu, con
   }
 }
 
-// ---- head: 3x3, C -> 1, fp32 out ---------------------------------------------------------------------
+// ---- head tile geometry ------------------------------------------------------------------------------------
 constexpr int HT = 16, HP = HT + 2;
-template <int C>
+
+// ---- head on tensor cores: 3x3, 64 -> 1, fp32 out ---------------------------------------------------------
+// The CUDA-core version of this layer issued 1700 instructions per pixel (576 FMAs + 570 bf16 unpacks + 216 LDS.128) and
+// ran at 1.4 TB/s.  Here a warp computes 16 pixels of a row with mma.sync.m16n8k16 (bf16 -> fp32): A = 16 pixels x
+// 16 channels straight out of the shared-memory patch (ldmatrix.x4), B = 16 channels x 8 columns of which column 0
+// holds bf16(w) and column 1 holds bf16(w - bf16(w)) (the weights keep ~16 mantissa bits; eps feeds the SDE
+// update directly), 36 MMAs per 16 pixels.  tcgen05 would spend a 64-cycle M128 slot per K=16 step on an N=8
+// problem; the legacy warp-level MMA is the right size for this 0.04 %-of-FLOPs layer.
+constexpr int HM_PITCH = 64 * 2 + 16;                              // bytes per patch pixel (ldmatrix rows: conflict-free)
+constexpr int HM_WFRAG = 36 * 32 * 8;                              // [tap*4 + kchunk][lane] -> (b0, b1)
+constexpr int HM_SMEM = HM_WFRAG + HP * HP * HM_PITCH;
+
 __global__ void __launch_bounds__(256)
-head_conv3_kernel(const __nv_bfloat16* __restrict__ src, const float* __restrict__ w, float bias,
-                  float* __restrict__ out, int H, int W) {
-  constexpr int PITCH = C * 2 + 16;                              // bytes per patch pixel (+16: bank spread)
+head_conv3_mma_kernel(const __nv_bfloat16* __restrict__ src, const uint4* __restrict__ wpk, float bias,
+                      float* __restrict__ out, int H, int W) {
   extern __shared__ __align__(16) uint8_t hsm[];
-  float* ws = reinterpret_cast<float*>(hsm);                     // [9][C]
-  uint8_t* patch = hsm + 9 * C * 4;
+  uint2* wfrag = reinterpret_cast<uint2*>(hsm);
+  uint8_t* patch = hsm + HM_WFRAG;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, oy0 = blockIdx.y * HT, ox0 = blockIdx.x * HT;
-  for (int i = threadIdx.x; i < 9 * C; i += 256) ws[i] = w[i];
-  constexpr int VPP = C / 8;
-  for (int i = threadIdx.x; i < HP * HP * VPP; i += 256) {
+  // B fragments, pre-packed on the host (packing.py::pack_head_weight): lane holds k = 2*(lane%4) + {0,1} (b0) and
+  // k + 8 (b1) of column n = lane/4; column 0 = bf16(w), column 1 = bf16(w - bf16(w)), the rest zero
+  for (int i = tid; i < HM_WFRAG / 16; i += 256) reinterpret_cast<uint4*>(wfrag)[i] = __ldg(wpk + i);
+  constexpr int VPP = 8, NL = (HP * HP * VPP + 255) / 256;         // 11 vectors per thread, all in flight together
+  uint4 q[NL];
+#pragma unroll
+  for (int k = 0; k < NL; ++k) {
+    const int i = tid + 256 * k;
     const int pix = i / VPP, v = i - pix * VPP, py = pix / HP, px = pix - py * HP;
     const int iy = oy0 + py - 1, ix = ox0 + px - 1;
-    uint4 q = make_uint4(0u, 0u, 0u, 0u);
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-      q = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)b * H + iy) * W + ix) * C + v * 8));
-    *reinterpret_cast<uint4*>(patch + pix * PITCH + v * 16) = q;
+    q[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (i < HP * HP * VPP && iy >= 0 && iy < H && ix >= 0 && ix < W)
+      q[k] = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)b * H + iy) * W + ix) * 64 + v * 8));
+  }
+#pragma unroll
+  for (int k = 0; k < NL; ++k) {
+    const int i = tid + 256 * k;
+    if (i < HP * HP * VPP) *reinterpret_cast<uint4*>(patch + (i / VPP) * HM_PITCH + (i % VPP) * 16) = q[k];
   }
   __syncthreads();
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  float acc = bias;
+  const uint32_t patch_u = smem_u32(patch);
+  const int g = lane >> 2;
+#pragma unroll 1
+  for (int rr = 0; rr < 2; ++rr) {
+    const int ty = warp * 2 + rr;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    // ldmatrix row of this lane: pixel (lane & 15) of the row, 8-channel block (lane >> 4)
+    const uint32_t a_lane = patch_u + (uint32_t)((ty * HP + (lane & 15)) * HM_PITCH + (lane >> 4) * 16);
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
+    for (int tap = 0; tap < 9; ++tap) {
+      const uint32_t a_tap = a_lane + (uint32_t)(((tap / 3) * HP + (tap % 3)) * HM_PITCH);
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const uint8_t* pp = patch + ((ty + ky) * HP + tx + kx) * PITCH;
-      const float* wr = ws + (ky * 3 + kx) * C;
-#pragma unroll
-      for (int v = 0; v < VPP; ++v) {
-        float f[8];
-        unpack_bf16x8(*reinterpret_cast<const uint4*>(pp + v * 16), f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc = fmaf(f[e], wr[v * 8 + e], acc);
+      for (int kc = 0; kc < 4; ++kc) {
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(a_tap + kc * 32));
+        const uint2 bf = wfrag[(tap * 4 + kc) * 32 + lane];
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                     "{%0, %1, %2, %3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
       }
     }
-  const int oy = oy0 + ty, ox = ox0 + tx;
-  if (oy < H && ox < W) out[((size_t)b * H + oy) * W + ox] = acc;
+    if ((lane & 3) == 0) {                              // columns 0 (hi weights) and 1 (lo weights) of rows g, g + 8
+      const int oy = oy0 + ty;
+      if (oy < H) {
+        float* orow = out + ((size_t)b * H + oy) * W;
+        if (ox0 + g < W) orow[ox0 + g] = c[0] + c[1] + bias;
+        if (ox0 + g + 8 < W) orow[ox0 + g + 8] = c[2] + c[3] + bias;
+      }
+    }
+  }
 }
 
 // ---- reference conv (tests only): one thread per (pixel, output channel) ----------------------------------
@@ -152,18 +186,18 @@ int idiff_stem_conv7(const float* x, const float* mu, const float* w, const floa
   return check_launch("stem_conv7");
 }
 
-int idiff_head_conv3(const void* src, const float* w, float bias, float* out, int B, int H, int W, int C,
+int idiff_head_conv3(const void* src, const void* w, float bias, float* out, int B, int H, int W, int C,
                      void* stream) {
-  IDIFF_REQUIRE(src && w && out && B > 0 && H > 0 && W > 0, "head_conv3: bad arguments");
+  IDIFF_REQUIRE(src && w && out && B > 0 && H > 0 && W > 0 && aligned16(w) && aligned16(src), "head_conv3: bad arguments");
   IDIFF_REQUIRE(C == 64, "head_conv3: C must be 64 (got %d)", C);
   dim3 grid((W + HT - 1) / HT, (H + HT - 1) / HT, B);
-  const int smem = 9 * 64 * 4 + HP * HP * (64 * 2 + 16);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(head_conv3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(head_conv3_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HM_SMEM);
+    if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "head_conv3 attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  head_conv3_kernel<64><<<grid, 256, smem, as_stream(stream)>>>((const __nv_bfloat16*)src, w, bias, out, H, W);
+  head_conv3_mma_kernel<<<grid, 256, HM_SMEM, as_stream(stream)>>>((const __nv_bfloat16*)src, (const uint4*)w, bias, out, H, W);
   return check_launch("head_conv3");
 }
 

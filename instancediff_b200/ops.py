@@ -82,9 +82,12 @@ def stem_conv7_tc(x, mu, w, bias):
 
 
 def head_conv3(src, w_hwc, bias: float):
+    """w_hwc: fp32 [3,3,64] (or [1,64,3,3]); packed into MMA fragments here (the UNet packs once per weight load)."""
+    from .packing import pack_head_weight
     B, H, W, Cc = src.shape
     out = torch.empty(B, 1, H, W, dtype=torch.float32, device=src.device)
-    check(_lib.lib().idiff_head_conv3(src.data_ptr(), w_hwc.data_ptr(), float(bias), out.data_ptr(), B, H, W, Cc,
+    wp = pack_head_weight(w_hwc.float()).to(src.device)
+    check(_lib.lib().idiff_head_conv3(src.data_ptr(), wp.data_ptr(), float(bias), out.data_ptr(), B, H, W, Cc,
                                       _s(src)), "head_conv3")
     return out
 

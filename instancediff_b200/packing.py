@@ -76,3 +76,24 @@ def pack_stem_weight(w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     wk[:, 99] = bias - b_hi
     full = torch.cat([wk, lo_half], dim=1)                      # [N, 224]
     return full.reshape(N, 28, 8).permute(1, 0, 2).contiguous().to(torch.bfloat16).reshape(-1)
+
+
+def pack_head_weight(w: torch.Tensor) -> torch.Tensor:
+    """Head 3x3 conv weights (w: [1, 64, 3, 3] or [3, 3, 64] fp32) -> the mma.sync.m16n8k16 B fragments
+    idiff_head_conv3 loads: [36 chunks = tap*4 + k-chunk][32 lanes][b0, b1] uint32, where lane holds
+    k = 2*(lane%4) + {0,1} (b0) and k + 8 (b1) of column n = lane//4; column 0 = bf16(w), column 1 = bf16(w - bf16(w))
+    (the fp32 weights keep ~16 mantissa bits), columns 2..7 zero.  Returned as a bf16 tensor of 4608 elements."""
+    if w.dim() == 4:
+        w = w[0].permute(1, 2, 0)                                   # [3, 3, 64]
+    wk = w.reshape(9, 4, 16).float()                                # [tap][k-chunk][k]
+    hi = wk.to(torch.bfloat16)
+    lo = (wk - hi.float()).to(torch.bfloat16)
+    frag = torch.zeros(9, 4, 32, 4, dtype=torch.bfloat16, device=w.device)      # [tap][kc][lane][b0.lo, b0.hi, b1.lo, b1.hi]
+    for lane in range(8):                                           # only columns n = 0 (lanes 0-3) and 1 (lanes 4-7)
+        src = hi if lane < 4 else lo
+        k0 = (lane % 4) * 2
+        frag[:, :, lane, 0] = src[:, :, k0]
+        frag[:, :, lane, 1] = src[:, :, k0 + 1]
+        frag[:, :, lane, 2] = src[:, :, k0 + 8]
+        frag[:, :, lane, 3] = src[:, :, k0 + 9]
+    return frag.reshape(-1).contiguous()

@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 from ._lib import EPI_GEGLU, EPI_LN_OUT, EPI_PLAIN, EPI_QSOFTMAX, GemmParams, check
-from .packing import fold_layernorm, interleave_geglu, pack_conv_weight, pack_stem_weight
+from .packing import fold_layernorm, interleave_geglu, pack_conv_weight, pack_head_weight, pack_stem_weight
 
 GN_GROUPS = 8
 TILE_H, TILE_W = 16, 8
@@ -245,7 +245,7 @@ class ConditionalUNet:
 
         # stem / head / time
         pk["init_conv"] = dict(w=pack_stem_weight(f32(P["init_conv.weight"]), f32(P["init_conv.bias"])).to(self.device))
-        pk["final_conv"] = dict(w=f32(P["final_conv.weight"][0].permute(1, 2, 0)),
+        pk["final_conv"] = dict(w=pack_head_weight(f32(P["final_conv.weight"])).to(self.device),
                                 bias=float(P["final_conv.bias"].reshape(-1)[0].item()))
         self._res_names: List[str] = []
         n = len(self.io)

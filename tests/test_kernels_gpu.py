@@ -52,10 +52,13 @@ def test_stem_conv7_tensor_core(shape):
     assert rel_err(out, simt) <= 8e-3          # two bf16-rounded results may differ by one ulp (2^-7)
 
 
-def test_head_conv3():
+@pytest.mark.parametrize("shape", [(2, 24, 40), (1, 16, 16), (1, 21, 13), (3, 64, 64)])
+def test_head_conv3(shape):
+    """Head 3x3 conv on mma.sync with hi/lo-split weights: fp32-level agreement with the fp32 convolution of the same
+    bf16 activations; ragged and single-tile shapes included."""
     from instancediff_b200 import ops
     g = torch.Generator().manual_seed(1)
-    B, H, W = 2, 24, 40
+    B, H, W = shape
     src = rand_act(B, H, W, 64, g)
     w = ((torch.rand(1, 64, 3, 3, generator=g) * 2 - 1) / 24).cuda()
     out = ops.head_conv3(src, w[0].permute(1, 2, 0).contiguous(), 0.25)
