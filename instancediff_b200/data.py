@@ -94,3 +94,30 @@ def save_triptych(LQ, pred, GT, result_root: str, name: str, index: int) -> str:
     path = os.path.join(out_dir, f"{index}_{to_save.shape[-1]}x{to_save.shape[-2]}x1.raw")
     to_save.tofile(path)
     return path
+
+
+# ---- synthetic data set (no data ships with the reference snapshot) ---------------------------------------------
+MODALITY_NAMES = ["speckle in OCT", "scatter artifact in CT", "noise in cryo-EM image", "speckle in ultra sound"]
+
+
+def make_synthetic_dataset(root: str, seed: int = 7) -> str:
+    """Writes six seeded `.raw` items (A, B, A_emb) whose value ranges exercise every clamp of
+    ``normalize_modality`` plus a JSON file list under ``root``; returns the file-list path.  Used by the parity
+    fixtures (``oracle/gen_golden_io.py``), the tests and ``tools/test_um.py``."""
+    rng = np.random.default_rng(seed)
+    items = []
+    for i, name in enumerate(MODALITY_NAMES + MODALITY_NAMES[:2]):
+        scale = {"scatter artifact in CT": 2400.0, "noise in cryo-EM image": 320.0}.get(name, 1.0)
+        a = (rng.standard_normal((RAW_SIDE, RAW_SIDE)) * 0.35 + 0.5).astype(np.float32) * np.float32(scale)
+        b = (rng.random((RAW_SIDE, RAW_SIDE)) * 1.1 - 0.05).astype(np.float32) * np.float32(scale)
+        emb = rng.standard_normal(512).astype(np.float32)
+        paths = {}
+        for key, arr in (("A", a), ("B", b), ("A_emb", emb)):
+            p = os.path.join(root, f"item{i}_{key}.raw")
+            arr.tofile(p)
+            paths[key] = p
+        items.append(dict(paths, name=name))
+    flist = os.path.join(root, "flist.json")
+    with open(flist, "w") as f:
+        json.dump({"test": items, "train": items[:2]}, f)
+    return flist

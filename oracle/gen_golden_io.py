@@ -13,27 +13,8 @@ import tempfile
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-NAMES = ["speckle in OCT", "scatter artifact in CT", "noise in cryo-EM image", "speckle in ultra sound"]
-
-
-def make_inputs(root, seed=7):
-    """Seeded synthetic raw files with values that exercise every clamp: returns the JSON file-list path."""
-    rng = np.random.default_rng(seed)
-    items = []
-    for i, name in enumerate(NAMES + NAMES[:2]):
-        scale = {"scatter artifact in CT": 2400.0, "noise in cryo-EM image": 320.0}.get(name, 1.0)
-        a = (rng.standard_normal((224, 224)) * 0.35 + 0.5).astype(np.float32) * np.float32(scale)
-        b = (rng.random((224, 224)) * 1.1 - 0.05).astype(np.float32) * np.float32(scale)
-        emb = rng.standard_normal(512).astype(np.float32)
-        paths = {}
-        for key, arr in (("A", a), ("B", b), ("A_emb", emb)):
-            p = os.path.join(root, f"item{i}_{key}.raw")
-            arr.tofile(p)
-            paths[key] = p
-        items.append(dict(paths, name=name))
-    flist = os.path.join(root, "flist.json")
-    json.dump({"test": items, "train": items[:2]}, open(flist, "w"))
-    return flist
+sys.path.insert(0, os.path.join(HERE, ".."))
+from instancediff_b200.data import MODALITY_NAMES as NAMES, make_synthetic_dataset as make_inputs  # noqa: E402,F401
 
 
 def digest(t):

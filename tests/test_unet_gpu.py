@@ -225,7 +225,7 @@ def test_testum_style_driver_end_to_end(tmp_path):
     import importlib.util
     import os
     import numpy as np
-    from oracle.gen_golden_io import NAMES, make_inputs
+    from instancediff_b200.data import MODALITY_NAMES as NAMES, make_synthetic_dataset as make_inputs
     spec = importlib.util.spec_from_file_location("test_um", os.path.join(os.path.dirname(__file__), "..", "tools", "test_um.py"))
     drv = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(drv)

@@ -71,10 +71,9 @@ def main():
     args = ap.parse_args()
     tmp = None
     if args.flist is None:
-        from oracle.gen_golden_io import NAMES, make_inputs            # synthetic `.raw` files (test infrastructure)
         tmp = tempfile.TemporaryDirectory()
-        args.flist = make_inputs(tmp.name)
-        args.artifact_type = args.artifact_type or NAMES[:2]
+        args.flist = D.make_synthetic_dataset(tmp.name)
+        args.artifact_type = args.artifact_type or D.MODALITY_NAMES[:2]
         args.max_items = min(args.max_items, 2)
     root = args.result_root or os.path.join(tempfile.gettempdir(), "idiff_results")
     run(args.flist, root, args.artifact_type or [], args.weights, args.max_items, args.T)
