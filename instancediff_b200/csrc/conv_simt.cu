@@ -76,63 +76,75 @@ constexpr int HM_PITCH = 64 * 2 + 16;                              // bytes per 
 constexpr int HM_WFRAG = 36 * 32 * 8;                              // [tap*4 + kchunk][lane] -> (b0, b1)
 constexpr int HM_SMEM = HM_WFRAG + HP * HP * HM_PITCH;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 head_conv3_mma_kernel(const __nv_bfloat16* __restrict__ src, const uint4* __restrict__ wpk, float bias,
-                      float* __restrict__ out, int H, int W) {
+                      float* __restrict__ out, int H, int W, int tiles_x, int tiles_y, int total) {
   extern __shared__ __align__(16) uint8_t hsm[];
   uint2* wfrag = reinterpret_cast<uint2*>(hsm);
   uint8_t* patch = hsm + HM_WFRAG;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.z, oy0 = blockIdx.y * HT, ox0 = blockIdx.x * HT;
   // B fragments, pre-packed on the host (packing.py::pack_head_weight): lane holds k = 2*(lane%4) + {0,1} (b0) and
   // k + 8 (b1) of column n = lane/4; column 0 = bf16(w), column 1 = bf16(w - bf16(w)), the rest zero
   for (int i = tid; i < HM_WFRAG / 16; i += 256) reinterpret_cast<uint4*>(wfrag)[i] = __ldg(wpk + i);
-  constexpr int VPP = 8, NL = (HP * HP * VPP + 255) / 256;         // 11 vectors per thread, all in flight together
+  // Persistent CTA: the NEXT tile's patch (11 x 16 B per thread) is in flight while the current one is multiplied
+  // (one tile per CTA spent half of its life waiting for its own loads).
+  constexpr int VPP = 8, NL = (HP * HP * VPP + 255) / 256;
   uint4 q[NL];
+  auto fetch = [&](int tile) {
+    const int tx = tile % tiles_x, r = tile / tiles_x, ty = r % tiles_y, b = r / tiles_y;
+    const int oy0 = ty * HT, ox0 = tx * HT;
 #pragma unroll
-  for (int k = 0; k < NL; ++k) {
-    const int i = tid + 256 * k;
-    const int pix = i / VPP, v = i - pix * VPP, py = pix / HP, px = pix - py * HP;
-    const int iy = oy0 + py - 1, ix = ox0 + px - 1;
-    q[k] = make_uint4(0u, 0u, 0u, 0u);
-    if (i < HP * HP * VPP && iy >= 0 && iy < H && ix >= 0 && ix < W)
-      q[k] = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)b * H + iy) * W + ix) * 64 + v * 8));
-  }
-#pragma unroll
-  for (int k = 0; k < NL; ++k) {
-    const int i = tid + 256 * k;
-    if (i < HP * HP * VPP) *reinterpret_cast<uint4*>(patch + (i / VPP) * HM_PITCH + (i % VPP) * 16) = q[k];
-  }
-  __syncthreads();
+    for (int k = 0; k < NL; ++k) {
+      const int i = tid + 256 * k;
+      const int pix = i / VPP, v = i - pix * VPP, py = pix / HP, px = pix - py * HP;
+      const int iy = oy0 + py - 1, ix = ox0 + px - 1;
+      q[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < HP * HP * VPP && iy >= 0 && iy < H && ix >= 0 && ix < W)
+        q[k] = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)b * H + iy) * W + ix) * 64 + v * 8));
+    }
+  };
   const uint32_t patch_u = smem_u32(patch);
   const int g = lane >> 2;
-#pragma unroll 1
-  for (int rr = 0; rr < 2; ++rr) {
-    const int ty = warp * 2 + rr;
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
-    // ldmatrix row of this lane: pixel (lane & 15) of the row, 8-channel block (lane >> 4)
-    const uint32_t a_lane = patch_u + (uint32_t)((ty * HP + (lane & 15)) * HM_PITCH + (lane >> 4) * 16);
+  if ((int)blockIdx.x < total) fetch(blockIdx.x);
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int tx = tile % tiles_x, r = tile / tiles_x, ty0 = r % tiles_y, b = r / tiles_y;
+    const int oy0 = ty0 * HT, ox0 = tx * HT;
+    __syncthreads();                                   // every warp is done with the previous patch
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const uint32_t a_tap = a_lane + (uint32_t)(((tap / 3) * HP + (tap % 3)) * HM_PITCH);
-#pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {
-        uint32_t a0, a1, a2, a3;
-        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(a_tap + kc * 32));
-        const uint2 bf = wfrag[(tap * 4 + kc) * 32 + lane];
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-                     "{%0, %1, %2, %3};"
-                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
-      }
+    for (int k = 0; k < NL; ++k) {
+      const int i = tid + 256 * k;
+      if (i < HP * HP * VPP) *reinterpret_cast<uint4*>(patch + (i / VPP) * HM_PITCH + (i % VPP) * 16) = q[k];
     }
-    if ((lane & 3) == 0) {                              // columns 0 (hi weights) and 1 (lo weights) of rows g, g + 8
-      const int oy = oy0 + ty;
-      if (oy < H) {
-        float* orow = out + ((size_t)b * H + oy) * W;
-        if (ox0 + g < W) orow[ox0 + g] = c[0] + c[1] + bias;
-        if (ox0 + g + 8 < W) orow[ox0 + g + 8] = c[2] + c[3] + bias;
+    __syncthreads();
+    if (tile + (int)gridDim.x < total) fetch(tile + gridDim.x);
+#pragma unroll 1
+    for (int rr = 0; rr < 2; ++rr) {
+      const int ty = warp * 2 + rr;
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      // ldmatrix row of this lane: pixel (lane & 15) of the row, 8-channel block (lane >> 4)
+      const uint32_t a_lane = patch_u + (uint32_t)((ty * HP + (lane & 15)) * HM_PITCH + (lane >> 4) * 16);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const uint32_t a_tap = a_lane + (uint32_t)(((tap / 3) * HP + (tap % 3)) * HM_PITCH);
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+          uint32_t a0, a1, a2, a3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(a_tap + kc * 32));
+          const uint2 bf = wfrag[(tap * 4 + kc) * 32 + lane];
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                       "{%0, %1, %2, %3};"
+                       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
+        }
+      }
+      if ((lane & 3) == 0) {                              // columns 0 (hi weights) and 1 (lo weights) of rows g, g + 8
+        const int oy = oy0 + ty;
+        if (oy < H) {
+          float* orow = out + ((size_t)b * H + oy) * W;
+          if (ox0 + g < W) orow[ox0 + g] = c[0] + c[1] + bias;
+          if (ox0 + g + 8 < W) orow[ox0 + g + 8] = c[2] + c[3] + bias;
+        }
       }
     }
   }
@@ -190,14 +202,19 @@ int idiff_head_conv3(const void* src, const void* w, float bias, float* out, int
                      void* stream) {
   IDIFF_REQUIRE(src && w && out && B > 0 && H > 0 && W > 0 && aligned16(w) && aligned16(src), "head_conv3: bad arguments");
   IDIFF_REQUIRE(C == 64, "head_conv3: C must be 64 (got %d)", C);
-  dim3 grid((W + HT - 1) / HT, (H + HT - 1) / HT, B);
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(head_conv3_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HM_SMEM);
-    if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "head_conv3 attr: %s", cudaGetErrorString(e));
-    attr = true;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(head_conv3_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HM_SMEM);
+    if (e != cudaSuccess) { num_sms = 0; return fail(IDIFF_ERR_CUDA, "head_conv3 setup: %s", cudaGetErrorString(e)); }
   }
-  head_conv3_mma_kernel<<<grid, 256, HM_SMEM, as_stream(stream)>>>((const __nv_bfloat16*)src, (const uint4*)w, bias, out, H, W);
+  const int tiles_x = (W + HT - 1) / HT, tiles_y = (H + HT - 1) / HT, total = tiles_x * tiles_y * B;
+  const int grid = total < 2 * num_sms ? total : 2 * num_sms;       // 2 resident CTAs per SM (114 registers per thread)
+  head_conv3_mma_kernel<<<grid, 256, HM_SMEM, as_stream(stream)>>>((const __nv_bfloat16*)src, (const uint4*)w, bias, out, H, W,
+                                                                   tiles_x, tiles_y, total);
   return check_launch("head_conv3");
 }
 
