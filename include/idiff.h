@@ -52,6 +52,15 @@ int idiff_sde_step(float* x_out, const float* x, const float* eps, const float* 
                    const float* coef, int input_is_score, int use_philox, uint64_t seed,
                    uint64_t elem_offset, size_t n, void* stream);
 
+/* Same update with in-kernel Philox noise, but {seed, elem_offset} are read from DEVICE memory
+ * (rng_dev[0], rng_dev[1]) at run time, so a CUDA graph captured once serves every item of a
+ * testUM.py-style loop (testUM.py:126-146: one reverse process per data-set item, each with its own
+ * noise stream) after a 16-byte device write.  offset_is_multiple_of_4 is the caller's promise
+ * about rng_dev[1] for every replay; it selects the float4 path (0 is always safe). */
+int idiff_sde_step_rng(float* x_out, const float* x, const float* eps, const float* mu, const float* coef,
+                       int input_is_score, const uint64_t* rng_dev, int offset_is_multiple_of_4, size_t n,
+                       void* stream);
+
 /* Builds the per-t coefficient rows {theta, sigma, sigma_bar, dt, sqrt_dt, 0,0,0} (8 floats per
  * t, T1 = T+1 rows) from the reference's tables (utils/sde_utils.py:149-152) on the HOST. */
 int idiff_sde_pack_table(const float* theta_host, const float* sigma_host, const float* sigma_bar_host,
@@ -60,6 +69,18 @@ int idiff_sde_pack_table(const float* theta_host, const float* sigma_host, const
 /* x_T = mu + z * max_sigma            IRSDE.noise_state  utils/sde_utils.py:340-341 */
 int idiff_noise_state(float* x_out, const float* mu, const float* z, float max_sigma, int use_philox,
                       uint64_t seed, uint64_t elem_offset, size_t n, void* stream);
+
+/* Forward-process training states of IRSDE.generate_random_states (utils/sde_utils.py:322-338) with
+ * IRSDE.mu_bar (:169-170) folded in, one pass:
+ *   x_t[b] = z * sigma_bar[b] + (mu + (x0 - mu) * decay[b]),   decay[b] = exp(-thetas_cumsum[t_b] * dt)
+ * decay / sigma_bar: per-sample fp32 DEVICE arrays [n / per_sample] (gathered from the schedule tables by
+ * the caller, as the reference's `self.thetas_cumsum[t]` / `self.sigma_bars[t]` indexing does).  z: pre-drawn
+ * N(0,1) or NULL with use_philox != 0 (stream (seed, elem_offset + i), step word `step_word`).  z_out
+ * (optional) receives the noise that was used -- the target of the noise-matching loss
+ * (IRSDE.get_real_noise, :222-223, returns it up to rounding).  Same fp32 operation order as the reference. */
+int idiff_random_states(float* xt_out, float* z_out, const float* x0, const float* mu, const float* z,
+                        const float* decay, const float* sigma_bar, int use_philox, uint64_t seed,
+                        uint64_t elem_offset, uint32_t step_word, size_t per_sample, size_t n, void* stream);
 
 /* Standard normal draws with the same Philox stream the fused step uses (tests / host parity). */
 int idiff_philox_normal(float* out, uint64_t seed, uint64_t elem_offset, uint32_t step, size_t n, void* stream);

@@ -43,9 +43,12 @@ SIGNATURES = {
     "idiff_watchdog_status": (C.c_int, [C.c_int]),
     "idiff_sde_step": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_uint64,
                                  C.c_uint64, C.c_size_t, c_ptr]),
+    "idiff_sde_step_rng": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, C.c_int, C.c_size_t, c_ptr]),
     "idiff_sde_pack_table": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_float, C.c_double, c_ptr]),
     "idiff_noise_state": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_float, C.c_int, C.c_uint64, C.c_uint64,
                                     C.c_size_t, c_ptr]),
+    "idiff_random_states": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_uint64, C.c_uint64,
+                                      C.c_uint32, C.c_size_t, C.c_size_t, c_ptr]),
     "idiff_philox_normal": (C.c_int, [c_ptr, C.c_uint64, C.c_uint64, C.c_uint32, C.c_size_t, c_ptr]),
     "idiff_step_select": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_float, c_ptr]),
     "idiff_set_debug_flags": (C.c_int, [C.c_int]),

@@ -65,7 +65,12 @@ template <bool kVec>
 __global__ void __launch_bounds__(256)
 sde_step_kernel(float* __restrict__ xo, const float* __restrict__ x, const float* __restrict__ eps,
                 const float* __restrict__ mu, const float* __restrict__ z, const float* __restrict__ coef,
-                int is_score, int philox, uint64_t seed, uint64_t elem_offset, size_t n) {
+                int is_score, int philox, uint64_t seed, uint64_t elem_offset, const uint64_t* __restrict__ rng_dev,
+                size_t n) {
+  if (rng_dev) {                       // {seed, elem_offset} in device memory: one captured graph serves every item
+    seed = __ldg(rng_dev);
+    elem_offset = __ldg(rng_dev + 1);
+  }
   StepCoef c;
   c.theta = __ldg(coef + 0);
   c.sigma = __ldg(coef + 1);
@@ -125,6 +130,57 @@ sde_step_kernel(float* __restrict__ xo, const float* __restrict__ x, const float
   }
 }
 
+// Forward-process training states (utils/sde_utils.py:169-170, 331-336): per sample b with its own timestep,
+//   state_mean = mu + (x0 - mu) * decay[b]          decay[b] = exp(-thetas_cumsum[t_b] * dt)   (:170)
+//   x_t        = z * sbar[b] + state_mean           sbar[b]  = sigma_bars[t_b]                 (:334-336)
+// One pass instead of the reference's 5 elementwise launches; same fp32 operation order, no FMA contraction.
+IDIFF_DEVINL float random_state(float x0, float mu, float z, float decay, float sbar) {
+  const float mean = __fadd_rn(mu, __fmul_rn(__fsub_rn(x0, mu), decay));
+  return __fadd_rn(__fmul_rn(z, sbar), mean);
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(256)
+random_states_kernel(float* __restrict__ xt, float* __restrict__ z_out, const float* __restrict__ x0,
+                     const float* __restrict__ mu, const float* __restrict__ z, const float* __restrict__ decay,
+                     const float* __restrict__ sbar, int philox, uint64_t seed, uint64_t elem_offset, uint32_t step,
+                     size_t per_sample, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (kVec) {
+    const size_t n4 = n >> 2, ps4 = per_sample >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const size_t b = i / ps4;
+      const float d = __ldg(decay + b), sb = __ldg(sbar + b);
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(x0) + i);
+      const float4 m = __ldcs(reinterpret_cast<const float4*>(mu) + i);
+      const float4 q = philox ? philox_normal4(seed, (elem_offset >> 2) + i, step)
+                              : __ldcs(reinterpret_cast<const float4*>(z) + i);
+      float4 o;
+      o.x = random_state(a.x, m.x, q.x, d, sb);
+      o.y = random_state(a.y, m.y, q.y, d, sb);
+      o.z = random_state(a.z, m.z, q.z, d, sb);
+      o.w = random_state(a.w, m.w, q.w, d, sb);
+      reinterpret_cast<float4*>(xt)[i] = o;
+      if (z_out) reinterpret_cast<float4*>(z_out)[i] = q;
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const size_t b = i / per_sample;
+      float zv;
+      if (philox) {
+        const uint64_t g = elem_offset + i;
+        const float4 q = philox_normal4(seed, g >> 2, step);
+        const int l = (int)(g & 3);
+        zv = l == 0 ? q.x : l == 1 ? q.y : l == 2 ? q.z : q.w;
+      } else {
+        zv = z[i];
+      }
+      xt[i] = random_state(x0[i], mu[i], zv, __ldg(decay + b), __ldg(sbar + b));
+      if (z_out) z_out[i] = zv;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 noise_state_kernel(float* __restrict__ xo, const float* __restrict__ mu, const float* __restrict__ z,
                    float max_sigma, int philox, uint64_t seed, uint64_t elem_offset, size_t n) {
@@ -178,14 +234,14 @@ static int grid_for(size_t work_items, int block) {
 
 extern "C" {
 
-int idiff_sde_step(float* x_out, const float* x, const float* eps, const float* mu, const float* z,
-                   const float* coef, int input_is_score, int use_philox, uint64_t seed, uint64_t elem_offset,
-                   size_t n, void* stream) {
+static int sde_step_launch(float* x_out, const float* x, const float* eps, const float* mu, const float* z,
+                           const float* coef, int input_is_score, int use_philox, uint64_t seed, uint64_t elem_offset,
+                           const uint64_t* rng_dev, bool offset_mult4, size_t n, void* stream) {
   using namespace idiff;
   if (n == 0) return IDIFF_OK;                       // empty batch: nothing to do (pointers may be null)
   IDIFF_REQUIRE(x_out && x && eps && coef, "sde_step: null pointer");
   const bool vec = (n % 4 == 0) && aligned16(x_out) && aligned16(x) && aligned16(eps) && (!mu || aligned16(mu)) &&
-                   (!z || aligned16(z)) && (elem_offset % 4 == 0);
+                   (!z || aligned16(z)) && offset_mult4;
   if (vec) {
     // exactly two float4 items per thread when the tensor is large enough: one balanced wave (<= 8 CTAs per SM)
     const size_t n4 = n / 4;
@@ -193,12 +249,28 @@ int idiff_sde_step(float* x_out, const float* x, const float* eps, const float* 
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     sde_step_kernel<true><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
-        x_out, x, eps, mu, z, coef, input_is_score, use_philox, seed, elem_offset, n);
+        x_out, x, eps, mu, z, coef, input_is_score, use_philox, seed, elem_offset, rng_dev, n);
   } else {
     sde_step_kernel<false><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
-        x_out, x, eps, mu, z, coef, input_is_score, use_philox, seed, elem_offset, n);
+        x_out, x, eps, mu, z, coef, input_is_score, use_philox, seed, elem_offset, rng_dev, n);
   }
   return check_launch("sde_step");
+}
+
+int idiff_sde_step(float* x_out, const float* x, const float* eps, const float* mu, const float* z,
+                   const float* coef, int input_is_score, int use_philox, uint64_t seed, uint64_t elem_offset,
+                   size_t n, void* stream) {
+  return sde_step_launch(x_out, x, eps, mu, z, coef, input_is_score, use_philox, seed, elem_offset, nullptr,
+                         elem_offset % 4 == 0, n, stream);
+}
+
+int idiff_sde_step_rng(float* x_out, const float* x, const float* eps, const float* mu, const float* coef,
+                       int input_is_score, const uint64_t* rng_dev, int offset_is_multiple_of_4, size_t n,
+                       void* stream) {
+  using namespace idiff;
+  IDIFF_REQUIRE(n == 0 || rng_dev, "sde_step_rng: null rng pointer");
+  return sde_step_launch(x_out, x, eps, mu, nullptr, coef, input_is_score, 1, 0, 0, rng_dev,
+                         offset_is_multiple_of_4 != 0, n, stream);
 }
 
 int idiff_sde_pack_table(const float* theta, const float* sigma, const float* sigma_bar, int T1, float dt,
@@ -238,6 +310,24 @@ int idiff_noise_state(float* x_out, const float* mu, const float* z, float max_s
   noise_state_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x_out, mu, z, max_sigma, use_philox, seed,
                                                                       elem_offset, n);
   return check_launch("noise_state");
+}
+
+int idiff_random_states(float* xt_out, float* z_out, const float* x0, const float* mu, const float* z,
+                        const float* decay, const float* sigma_bar, int use_philox, uint64_t seed,
+                        uint64_t elem_offset, uint32_t step_word, size_t per_sample, size_t n, void* stream) {
+  using namespace idiff;
+  if (n == 0) return IDIFF_OK;
+  IDIFF_REQUIRE(xt_out && x0 && mu && decay && sigma_bar && (z || use_philox), "random_states: null pointer");
+  IDIFF_REQUIRE(per_sample > 0 && n % per_sample == 0, "random_states: n must be a multiple of per_sample");
+  const bool vec = per_sample % 4 == 0 && elem_offset % 4 == 0 && aligned16(xt_out) && aligned16(x0) &&
+                   aligned16(mu) && (!z || aligned16(z)) && (!z_out || aligned16(z_out));
+  if (vec)
+    random_states_kernel<true><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
+        xt_out, z_out, x0, mu, z, decay, sigma_bar, use_philox, seed, elem_offset, step_word, per_sample, n);
+  else
+    random_states_kernel<false><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+        xt_out, z_out, x0, mu, z, decay, sigma_bar, use_philox, seed, elem_offset, step_word, per_sample, n);
+  return check_launch("random_states");
 }
 
 int idiff_philox_normal(float* out, uint64_t seed, uint64_t elem_offset, uint32_t step, size_t n, void* stream) {

@@ -34,6 +34,12 @@ def _stream(dev) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+def _as_i64(v: int) -> int:
+    """uint64 bit pattern as the int64 torch stores (the kernel reads it back as unsigned)."""
+    v = int(v) & 0xFFFFFFFFFFFFFFFF
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
 def _require_cuda_f32(name: str, t: torch.Tensor) -> torch.Tensor:
     if not torch.is_tensor(t) or not t.is_cuda:
         raise IdiffError(f"{name}: the fused SDE kernels need CUDA tensors (there is no CPU path)")
@@ -131,6 +137,7 @@ class IRSDE(SDE):
         self.philox_offset = 0          # global element index of this shard's first element
         self.use_cuda_graph = True
         self._graph_cache = {}
+        self.graph_cache_size = 4       # captured loops kept alive (one per state shape / model / device)
         self._table_dev = None
         self._initialize(self.max_sigma, self.sample_T, schedule, eps)
 
@@ -347,15 +354,22 @@ class IRSDE(SDE):
     def _reverse_sde_graph(self, xt, T, kwargs):
         dev = xt.device
         ctx = kwargs["image_context"]
-        key = (tuple(xt.shape), id(self.model), self.philox_seed, self.philox_offset)
-        st = self._graph_cache.get(key)
+        # the Philox stream {seed, offset} lives in device memory, so the captured graph does not depend on it:
+        # a data-set loop (one reverse process per item, each with its own offset) replays ONE graph
+        off4 = int(self.philox_offset) % 4 == 0
+        key = (tuple(xt.shape), id(self.model), str(dev), off4)
+        st = self._graph_cache.pop(key, None)
         L = _lib.lib()
         if st is None:
             st = dict(x=torch.empty_like(xt), mu=torch.empty_like(xt), ctx=ctx.detach().clone().to(dev),
                       counter=torch.zeros(1, dtype=torch.int32, device=dev),
                       row=torch.zeros(8, dtype=torch.float32, device=dev),
-                      time=torch.zeros(1, dtype=torch.float32, device=dev), graph=None)
-            self._graph_cache[key] = st
+                      time=torch.zeros(1, dtype=torch.float32, device=dev),
+                      rng=torch.zeros(2, dtype=torch.int64, device=dev), graph=None)
+            while len(self._graph_cache) >= self.graph_cache_size:      # oldest entry first (dicts keep order)
+                self._graph_cache.pop(next(iter(self._graph_cache)))
+        self._graph_cache[key] = st                                     # most recently used last
+        st["rng"].copy_(torch.tensor([_as_i64(self.philox_seed), _as_i64(self.philox_offset)], dtype=torch.int64))
         st["x"].copy_(xt)
         st["mu"].copy_(self._mu_tensor(xt))
         st["ctx"].copy_(ctx)
@@ -368,9 +382,9 @@ class IRSDE(SDE):
             check(L.idiff_step_select(table.data_ptr(), st["counter"].data_ptr(), st["row"].data_ptr(),
                                       st["time"].data_ptr(), float(self.sample_scale), s), "step_select")
             eps = self.model.forward_into(st["x"], st["mu"], None, st["ctx"], time_ptr=st["time"].data_ptr())
-            check(L.idiff_sde_step(st["x"].data_ptr(), st["x"].data_ptr(), eps.data_ptr(), st["mu"].data_ptr(), None,
-                                   st["row"].data_ptr(), 0, 1, self.philox_seed, self.philox_offset,
-                                   st["x"].numel(), s), "sde_step")
+            check(L.idiff_sde_step_rng(st["x"].data_ptr(), st["x"].data_ptr(), eps.data_ptr(), st["mu"].data_ptr(),
+                                       st["row"].data_ptr(), 0, st["rng"].data_ptr(), 1 if off4 else 0,
+                                       st["x"].numel(), s), "sde_step")
 
         done = 0
         if st["graph"] is None:
@@ -434,8 +448,27 @@ class IRSDE(SDE):
             batch = x0.shape[0]
             T_end = self.T + 1 if T_end <= 1 else T_end + 1
             timesteps = torch.randint(T_start, T_end, (batch, 1, 1, 1)).long()
-        state_mean = self.mu_bar(x0, timesteps)
-        noises = self._draw(-1, state_mean)
-        noise_level = self.sigma_bar(timesteps)
-        noisy_states = noises * noise_level + state_mean
+        # :331-336 in one fused pass (idiff_random_states); the per-sample coefficients are gathered from the
+        # schedule tables exactly as the reference indexes them (`thetas_cumsum[t]`, `sigma_bars[t]`)
+        x0 = _require_cuda_f32("x0", x0)
+        mu = _require_cuda_f32("mu", mu if tuple(mu.shape) == tuple(x0.shape) else mu.expand_as(x0))
+        dev = x0.device
+        B = x0.shape[0]
+        t_idx = torch.as_tensor(timesteps).to(dev).long().reshape(-1)
+        if t_idx.numel() == 1 and B != 1:
+            t_idx = t_idx.expand(B)
+        if t_idx.numel() != B:
+            raise IdiffError(f"generate_random_states: {t_idx.numel()} timesteps for a batch of {B}")
+        decay = torch.exp(-self.thetas_cumsum.to(dev)[t_idx] * self.dt).to(torch.float32).contiguous()   # :170
+        sbar = self.sigma_bars.to(dev)[t_idx].to(torch.float32).contiguous()                                      # :335
+        noisy_states = torch.empty_like(x0)
+        philox = self.noise_source == "philox"
+        z = None if philox else _require_cuda_f32("noise", self._draw(-1, x0))
+        self.last_noises = torch.empty_like(x0) if philox else z      # the noise-matching target (:222-223)
+        if B:
+            check(_lib.lib().idiff_random_states(
+                noisy_states.data_ptr(), self.last_noises.data_ptr() if philox else None, x0.data_ptr(), mu.data_ptr(),
+                None if philox else z.data_ptr(), decay.data_ptr(), sbar.data_ptr(), 1 if philox else 0,
+                self.philox_seed, self.philox_offset, 0xFFFFFFFE, x0.numel() // B, x0.numel(), _stream(dev)),
+                "random_states")
         return timesteps, noisy_states.to(torch.float32)

@@ -155,3 +155,66 @@ def test_training_state_helpers_match_reference_golden(loop):
     assert (xt.cpu() - torch.from_numpy(loop["train_xt"])).abs().max().item() < 1e-6
     eps = sde.get_real_noise(xt, x0t, ts)
     assert (eps.cpu() - torch.from_numpy(loop["train_eps"])).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(5, 1, 32, 32), (3, 1, 5, 7), (1, 1, 16, 16)])
+def test_random_states_kernel_is_bit_exact_vs_the_reference_expressions(shape):
+    """idiff_random_states == utils/sde_utils.py:331-336 evaluated op by op (mu_bar :170, then noises * level + mean)
+    on the same device tables; vector and scalar paths, per-sample timesteps."""
+    from instancediff_b200 import ops
+    sde = _sde()
+    g = torch.Generator().manual_seed(3)
+    B = shape[0]
+    x0 = (torch.rand(shape, generator=g) * 2 - 1).cuda()
+    mu = (torch.rand(shape, generator=g) * 2 - 1).cuda()
+    z = torch.randn(shape, generator=g).cuda()
+    ts = torch.randint(1, 101, (B, 1, 1, 1), generator=g)
+    sde.noise_source = lambda t, x: z
+    tt, xt = sde.generate_random_states(x0, mu, timesteps=ts)
+    assert tt is ts and xt.dtype == torch.float32
+    sde.set_mu(mu)
+    tdev = ts.cuda()
+    mean = sde.mu_bar(x0, tdev)                                  # :331  (torch ops, unfused)
+    ref = z * sde.sigma_bar(tdev) + mean                         # :333-336
+    assert torch.equal(xt, ref), (xt - ref).abs().max().item()
+    assert sde.last_noises is z or torch.equal(sde.last_noises, z)
+    # in-kernel Philox: the state is built from exactly the noise the kernel reports, which is the shared stream
+    sde.noise_source = "philox"
+    sde.philox_seed, sde.philox_offset = 11, 8 * x0[0].numel()
+    _, xt2 = sde.generate_random_states(x0, mu, timesteps=ts)
+    zz = ops.philox_normal(x0.numel(), "cuda", seed=11, offset=8 * x0[0].numel(), step=0xFFFFFFFE).reshape(shape)
+    assert torch.equal(sde.last_noises, zz)
+    assert torch.equal(xt2, zz * sde.sigma_bar(tdev) + mean)
+    # the noise-matching target recovered the reference's way (:222-223) agrees with the reported noise
+    eps = sde.get_real_noise(xt2, x0, tdev)
+    assert (eps - zz).abs().max().item() < 1e-3
+    # default timesteps: U{1..T} per sample, shape [B,1,1,1] long (:327-329)
+    t3, _ = sde.generate_random_states(x0, mu)
+    assert tuple(t3.shape) == (B, 1, 1, 1) and t3.dtype == torch.int64 and 1 <= int(t3.min()) and int(t3.max()) <= 100
+
+
+def test_random_states_rejects_cpu_tensors():
+    from instancediff_b200 import IRSDE, IdiffError
+    sde = IRSDE(max_sigma=0.4, T=100)          # device=None: `x0.to(self.device)` (:323-324) leaves the tensors on the host
+    with pytest.raises(IdiffError):
+        sde.generate_random_states(torch.zeros(1, 1, 4, 4), torch.zeros(1, 1, 4, 4), timesteps=torch.ones(1, 1, 1, 1).long())
+
+
+@pytest.mark.parametrize("n,offset", [(4096, 4096), (4096, 4099), (1001, 12)])
+def test_sde_step_with_device_side_rng_parameters(n, offset):
+    """idiff_sde_step_rng (seed/offset read from device memory) == idiff_sde_step with the same values."""
+    from instancediff_b200 import _lib, ops
+    sde = _sde()
+    g = torch.Generator().manual_seed(n + offset)
+    x, e, mu = (torch.randn(n, generator=g).cuda() for _ in range(3))
+    row = sde._coef_table(x.device)[37]
+    seed = 0xDEADBEEFCAFEF00D
+    want = ops.sde_step(x, e, mu, None, row, philox=True, seed=seed, offset=offset)
+    rng = torch.tensor([seed - (1 << 64), offset], dtype=torch.int64).cuda()
+    got = torch.empty_like(x)
+    s = torch.cuda.current_stream().cuda_stream
+    for promise in ([1, 0] if offset % 4 == 0 else [0]):
+        got.zero_()
+        _lib.check(_lib.lib().idiff_sde_step_rng(got.data_ptr(), x.data_ptr(), e.data_ptr(), mu.data_ptr(), row.data_ptr(),
+                                                 0, rng.data_ptr(), promise, n, s), "sde_step_rng")
+        assert torch.equal(got, want)

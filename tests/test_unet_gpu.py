@@ -258,3 +258,82 @@ def test_empty_batch_and_zero_steps(nets):
         e = sde.reverse_sde(x[:0], T=5, image_context=ctx[:0])
         assert tuple(e.shape) == (0, 1, 32, 32)
     assert tuple(net(x[:0], mu[:0], 3.0, image_context=ctx[:0]).shape) == (0, 1, 32, 32)
+
+
+def test_one_captured_graph_serves_every_item_of_a_dataset_loop(nets):
+    """The Philox stream is a device-side parameter of the captured step: items with different offsets replay the
+    same graph (no re-capture, no cache growth) and still equal the eager loop bit for bit."""
+    from instancediff_b200 import IRSDE
+    _, net = nets
+    B, H, W, T = 1, 32, 32, 6
+    _, mu, ctx = _inputs(B, H, W, seed=21)
+
+    def make(use_graph):
+        sde = IRSDE(0.4, T=100, schedule="cosine", eps=0.01, device=torch.device("cuda"))
+        sde.set_model(net)
+        sde.noise_source, sde.philox_seed, sde.use_cuda_graph = "philox", 5, use_graph
+        return sde
+
+    graph, eager = make(True), make(False)
+    for item, offset in enumerate([0, H * W, 7 * H * W, H * W]):
+        outs = []
+        for sde in (graph, eager):
+            m = mu + 0.01 * item
+            sde.set_mu(m)
+            sde.philox_offset = offset
+            outs.append(sde.reverse_sde(sde.noise_state(m), T=T, image_context=ctx))
+        assert torch.equal(outs[0], outs[1]), f"item {item}: {(outs[0] - outs[1]).abs().max():.3e}"
+        assert len(graph._graph_cache) == 1
+    # the cache is bounded: many distinct state shapes do not accumulate captured graphs
+    graph.graph_cache_size = 2
+    for h in (16, 32, 48):
+        _, m, c = _inputs(1, h, 32, seed=h)
+        graph.set_mu(m)
+        graph.reverse_sde(graph.noise_state(m), T=2, image_context=c)
+    assert len(graph._graph_cache) == 2
+
+
+def test_driver_protocol_with_checkpoint_round_trip(nets, tmp_path):
+    """testUM.py:74-146 on the drop-in objects: create_model -> save -> load (key clean-up of a DDP-style file, EMA
+    container) -> get_nets -> create_sde -> set_sde -> set_gpu -> feed_data -> test -> get_visuals; the result equals
+    calling IRSDE.reverse_sde directly with the same weights and noise stream."""
+    import numpy as np
+    from instancediff_b200 import IRSDE, checkpoint, create_model, create_sde
+    oracle, net = nets
+    sd = {k: v.detach().cpu() for k, v in oracle.state_dict().items()}
+    torch.save({"module." + k: v for k, v in sd.items()}, checkpoint.network_path(str(tmp_path), 1234, "NN"))
+    ema = {"initted": torch.tensor(True), "step": torch.tensor(9)}
+    ema.update({"online_model." + k: v for k, v in sd.items()})
+    ema.update({"ema_model." + k: v * 0.5 for k, v in sd.items()})
+    torch.save(ema, checkpoint.network_path(str(tmp_path), "lastest", "NN_ema"))
+
+    model = create_model({"dist": False}, {"use_image_context": True, "nnet_settings": {"nf": 64, "out_nc": 5, "text_module": "scoremap"}},
+                         phase="test", device="cuda", seed=3)
+    model.load(1234, str(tmp_path))
+    got_sd = model.get_nets(use_ema=False)["noise_net"].state_dict()
+    assert all(torch.equal(got_sd[k].cpu(), sd[k]) for k in sd)
+    ema_sd = model.get_nets(use_ema=True)["noise_net"].state_dict()
+    assert all(torch.equal(ema_sd[k].cpu(), sd[k] * 0.5) for k in sd)
+    sde = create_sde(model.get_nets(use_ema=False), dict(max_sigma=0.4, T=100, schedule="cosine", eps=0.01), device=torch.device("cuda"))
+    model.set_sde(sde)
+    model.set_gpu(torch.device("cuda:0"))
+    model.test_T = 5
+    x, mu, ctx = _inputs(1, 32, 32, seed=4)
+    vis = []
+    for item in range(2):
+        model.feed_data({"input": mu.cpu(), "target": mu.cpu(), "names": ["speckle in OCT"], "A_emb": ctx.cpu()})
+        model.test()
+        vis.append(model.get_visuals())
+        assert isinstance(vis[-1], np.ndarray) and vis[-1].shape == (1, 1, 32, 32) and vis[-1].dtype == np.float32
+    assert not np.array_equal(vis[0], vis[1])                       # every item draws from its own noise stream
+    ref = IRSDE(0.4, T=100, schedule="cosine", eps=0.01, device=torch.device("cuda"))
+    ref.set_model(net)
+    ref.noise_source, ref.philox_seed = "philox", 3
+    for item in range(2):
+        ref.set_mu(mu)
+        ref.philox_offset = item * mu.numel()
+        want = ref.reverse_sde(ref.noise_state(mu), T=5, image_context=ctx)
+        assert np.array_equal(vis[item], want.cpu().numpy())
+    # save() writes the reference's file names and the file loads back
+    model.save(77, str(tmp_path / "out"))
+    assert sorted(p.name for p in (tmp_path / "out").iterdir()) == ["77_NN.pth"]

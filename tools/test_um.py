@@ -17,37 +17,43 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from instancediff_b200 import ConditionalUNet, create_sde  # noqa: E402
+from instancediff_b200 import create_model, create_sde  # noqa: E402
 from instancediff_b200 import data as D  # noqa: E402
 
 
-def run(flist, result_root, artifact_types, weights=None, max_items=1000000, T=-1, seed=1, device="cuda:0"):
+def run(flist, result_root, artifact_types, weights=None, max_items=1000000, T=-1, seed=1, device="cuda:0",
+        pth_dir=None, iter_label=None, use_ema=False):
     torch.manual_seed(seed)                                           # testUM.py:35-43
     np.random.seed(seed)
     dev = torch.device(device)
-    net = ConditionalUNet(device=dev, seed=seed)
-    if weights:
-        net.load_state_dict(torch.load(weights, map_location="cpu"))
-    sde = create_sde({"noise_net": net}, dict(max_sigma=0.4, T=100, schedule="cosine", eps=0.01), device=dev)   # :91
-    sde.noise_source = "philox"
+    model = create_model({"dist": False}, {"use_image_context": True}, phase="test", device=dev, seed=seed)   # :74
+    if pth_dir is not None:
+        model.load(iter_label, pth_dir)                               # :76  {iter}_NN.pth (+ lastest_NN_ema.pth)
+    elif weights:
+        model.load_network(weights, model.noise_net)
+    sde_opt = dict(max_sigma=0.4, T=100, schedule="cosine", eps=0.01)
+    nets = model.get_nets(use_ema=use_ema)                            # :90
+    sde = create_sde(nets, sde_opt, device=dev)                       # :91
+    model.set_sde(sde)                                                # :92
+    model.set_gpu(dev)                                                # :95
+    model.test_T = T                                                  # debugging aid: run only the last T steps
     ds = D.SpeckleMedDataset(flist, phase="test", max_dataset_size=max_items, opt={"name": "test_b200"},
                              use_artifact_type=artifact_types)
     results = {}
     with torch.no_grad():                                             # :109
         for i in range(len(ds)):
             item = ds[i]
-            LQ, GT = item["LQ"][None].to(dev), item["GT"][None]       # [1,1,224,224], inputs in [-1, 1]
-            emb = item["A_emb"][None].to(dev)                         # [1,1,D]
-            sde.set_mu(LQ)
-            sde.philox_seed, sde.philox_offset = seed, i * LQ.numel()
+            LQ, GT = item["LQ"][None], item["GT"][None]               # [1,1,224,224], inputs in [-1, 1]
+            model.feed_data({"input": LQ.to(dev), "target": GT.to(dev), "names": [item["name"]],
+                             "A_emb": item["A_emb"][None].to(dev)})   # :128-139
             tic = time.time()
-            x0 = sde.reverse_sde(sde.noise_state(LQ), T=T, image_context=emb)
-            torch.cuda.synchronize(dev)
+            model.test()                                              # :142 (result lands on the host: synchronises)
             toc = time.time()
-            pred = D.to_unit_range(x0.detach().cpu().numpy())         # :151-152
+            visuals = model.get_visuals()                             # :146
+            pred = D.to_unit_range(visuals)                           # :151-152
             target = D.to_unit_range(GT.numpy())
             rmse, psnr = D.rmse_psnr(pred, target)
-            path = D.save_triptych(item["LQ"], x0, item["GT"], result_root, item["name"], i)
+            path = D.save_triptych(item["LQ"], torch.from_numpy(visuals), item["GT"], result_root, item["name"], i)
             r = results.setdefault(item["name"], dict(num=0, RMSE=[], PSNR=[], time=[]))
             r["num"] += 1
             r["RMSE"].append(rmse)
@@ -64,7 +70,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--flist", default=None)
     ap.add_argument("--result-root", default=None)
-    ap.add_argument("--weights", default=None)
+    ap.add_argument("--weights", default=None, help="a single noise-net state dict (.pth)")
+    ap.add_argument("--pth-dir", default=None, help="checkpoint directory holding {iter}_NN.pth (test.pth_dir)")
+    ap.add_argument("--iter", default=None, help="iteration label of the checkpoint (test.iter)")
+    ap.add_argument("--use-ema", action="store_true", help="sample with lastest_NN_ema.pth (test.use_ema)")
     ap.add_argument("--artifact-type", nargs="*", default=None)
     ap.add_argument("--max-items", type=int, default=1000000)
     ap.add_argument("--T", type=int, default=-1)
@@ -76,7 +85,8 @@ def main():
         args.artifact_type = args.artifact_type or D.MODALITY_NAMES[:2]
         args.max_items = min(args.max_items, 2)
     root = args.result_root or os.path.join(tempfile.gettempdir(), "idiff_results")
-    run(args.flist, root, args.artifact_type or [], args.weights, args.max_items, args.T)
+    run(args.flist, root, args.artifact_type or [], args.weights, args.max_items, args.T, pth_dir=args.pth_dir,
+        iter_label=args.iter, use_ema=args.use_ema)
 
 
 if __name__ == "__main__":
