@@ -396,15 +396,24 @@ def run_cuda(args):
 
 
 def main():
+    global RES, BATCH_PER_GPU, METRIC
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--res", type=int, default=RES, help="image side; 256 = the BASELINE metric's configuration, "
+                    "512 = the LoDoPaB-CT-shaped configs[3] (extra bench lines, not the headline)")
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU (32 = configs[1])")
     ap.add_argument("--cpu-steps", type=int, default=48, help="SDE steps of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-kernels", default=None, help="write the per-launch timing table (CSV) here")
     args = ap.parse_args()
+    if (args.res, args.batch) != (RES, BATCH_PER_GPU):
+        if args.res % 16 or args.res < 32 or args.batch < 1:
+            ap.error("--res must be a multiple of 16 (>= 32) and --batch >= 1")
+        METRIC = METRIC.replace(f"@{RES}^2", f"@{args.res}^2")
+        RES, BATCH_PER_GPU = args.res, args.batch
     if args.impl == "reference":
         run_reference(args)
     else:
