@@ -40,8 +40,11 @@ int idiff_watchdog_status(int clear);
  *   IRSDE.dispersion                             utils/sde_utils.py:184-185
  *   SDE.reverse_sde_step (/_mean)                utils/sde_utils.py:41-46
  * with one pass that keeps the reference's fp32 operation order (no FMA contraction):
- *   score = -eps / sigma_bar            (input_is_score != 0: `eps` already holds the score)
+ *   score = -eps / sigma_bar            (input_is_score bit 0: `eps` already holds the score)
  *   x_out = x - (theta*(mu-x) - sigma^2*score)*dt - sigma*(z*sqrt_dt)
+ * input_is_score bit 1 (value 2 or 3) selects the probability-flow ODE drift of
+ *   IRSDE.ode_reverse_drift / SDE.reverse_ode_step   utils/sde_utils.py:181-182, :48-49
+ *   x_out = x - (theta*(mu-x) - (0.5*sigma^2)*score)*dt      (pass z == NULL, use_philox == 0)
  * coef points at 5 floats {theta_t, sigma_t, sigma_bar_t, dt, sqrt_dt} in DEVICE memory
  * (a row of the table written by idiff_sde_pack_table), so one captured CUDA graph can be
  * replayed for every t.  z == NULL and use_philox == 0 gives the mean-only step (:41-42);

@@ -45,12 +45,14 @@ struct StepCoef {
   uint32_t step;
 };
 
-IDIFF_DEVINL float sde_update(float x, float e, float mu, float z, const StepCoef& c, bool is_score, bool has_noise) {
+// `flags`: bit 0 = `e` already holds the score; bit 1 = probability-flow ODE drift (:181-182) instead of :178-179
+IDIFF_DEVINL float sde_update(float x, float e, float mu, float z, const StepCoef& c, int flags, bool has_noise) {
   // utils/sde_utils.py:188   score = -noise / sigma_bar
-  const float score = is_score ? e : __fdiv_rn(-e, c.sbar);
-  // :179   (theta*(mu - x) - sigma**2 * score) * dt
+  const float score = (flags & 1) ? e : __fdiv_rn(-e, c.sbar);
+  // :179   (theta*(mu - x) - sigma**2 * score) * dt        :182   ... - 0.5 * sigma**2 * score ...
   const float t1 = __fmul_rn(c.theta, __fsub_rn(mu, x));
-  const float t2 = __fmul_rn(__fmul_rn(c.sigma, c.sigma), score);
+  const float s2 = __fmul_rn(c.sigma, c.sigma);
+  const float t2 = __fmul_rn((flags & 2) ? __fmul_rn(0.5f, s2) : s2, score);
   const float drift = __fmul_rn(__fsub_rn(t1, t2), c.dt);
   float out = __fsub_rn(x, drift);                       // :42 / :46 left-associated
   if (has_noise) {

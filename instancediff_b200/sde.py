@@ -220,8 +220,9 @@ class IRSDE(SDE):
         mu = torch.full_like(x, float(mu))
         return mu, mu.data_ptr()
 
-    def _fused_step(self, x, e, t, *, is_score, with_noise, out=None):
-        """x - drift - dispersion in one pass (replaces :45-46 + :178-179 + :184-185 + :187-188)."""
+    def _fused_step(self, x, e, t, *, is_score, with_noise, out=None, ode=False):
+        """x - drift - dispersion in one pass (replaces :45-46 + :178-179 + :184-185 + :187-188); ``ode`` selects the
+        probability-flow drift (:48-49 + :181-182, no dispersion)."""
         x = _require_cuda_f32("x", x)
         e = _require_cuda_f32("score/noise", e)
         if tuple(e.shape) != tuple(x.shape):
@@ -238,8 +239,8 @@ class IRSDE(SDE):
                 z = _require_cuda_f32("z", self._draw(t, x))
                 z_ptr = z.data_ptr()
         check(_lib.lib().idiff_sde_step(out.data_ptr(), x.data_ptr(), e.data_ptr(), mu_ptr, z_ptr, coef_ptr,
-                                        1 if is_score else 0, philox, self.philox_seed, self.philox_offset,
-                                        x.numel(), _stream(x.device)), "sde_step")
+                                        (1 if is_score else 0) | (2 if ode else 0), philox, self.philox_seed,
+                                        self.philox_offset, x.numel(), _stream(x.device)), "sde_step")
         return out
 
     def reverse_sde_step(self, x, score, t):              # :45-46
@@ -247,6 +248,9 @@ class IRSDE(SDE):
 
     def reverse_sde_step_mean(self, x, score, t):         # :41-42
         return self._fused_step(x, score, t, is_score=True, with_noise=False)
+
+    def reverse_ode_step(self, x, score, t):              # :48-49
+        return self._fused_step(x, score, t, is_score=True, with_noise=False, ode=True)
 
     def noise_state(self, tensor):                        # :340-341
         mu = _require_cuda_f32("tensor", tensor)
@@ -351,13 +355,13 @@ class IRSDE(SDE):
                 and hasattr(self.model, "forward_into") and set(kwargs) == {"image_context"}
                 and torch.is_tensor(self.mu))
 
-    def _reverse_sde_graph(self, xt, T, kwargs):
+    def _reverse_sde_graph(self, xt, T, kwargs, ode=False):
         dev = xt.device
         ctx = kwargs["image_context"]
         # the Philox stream {seed, offset} lives in device memory, so the captured graph does not depend on it:
         # a data-set loop (one reverse process per item, each with its own offset) replays ONE graph
         off4 = int(self.philox_offset) % 4 == 0
-        key = (tuple(xt.shape), id(self.model), str(dev), off4)
+        key = (tuple(xt.shape), id(self.model), str(dev), off4, ode)
         st = self._graph_cache.pop(key, None)
         L = _lib.lib()
         if st is None:
@@ -382,9 +386,13 @@ class IRSDE(SDE):
             check(L.idiff_step_select(table.data_ptr(), st["counter"].data_ptr(), st["row"].data_ptr(),
                                       st["time"].data_ptr(), float(self.sample_scale), s), "step_select")
             eps = self.model.forward_into(st["x"], st["mu"], None, st["ctx"], time_ptr=st["time"].data_ptr())
-            check(L.idiff_sde_step_rng(st["x"].data_ptr(), st["x"].data_ptr(), eps.data_ptr(), st["mu"].data_ptr(),
-                                       st["row"].data_ptr(), 0, st["rng"].data_ptr(), 1 if off4 else 0,
-                                       st["x"].numel(), s), "sde_step")
+            if ode:                                     # :48-49 -- no dispersion, half the sigma^2 * score term
+                check(L.idiff_sde_step(st["x"].data_ptr(), st["x"].data_ptr(), eps.data_ptr(), st["mu"].data_ptr(), None,
+                                       st["row"].data_ptr(), 2, 0, 0, 0, st["x"].numel(), s), "sde_step")
+            else:
+                check(L.idiff_sde_step_rng(st["x"].data_ptr(), st["x"].data_ptr(), eps.data_ptr(), st["mu"].data_ptr(),
+                                           st["row"].data_ptr(), 0, st["rng"].data_ptr(), 1 if off4 else 0,
+                                           st["x"].numel(), s), "sde_step")
 
         done = 0
         if st["graph"] is None:
@@ -403,16 +411,29 @@ class IRSDE(SDE):
         _lib.watchdog()
         return st["x"].clone()
 
-    def reverse_ode(self, xt, T=-1, save_states=False, save_dir="ode_state"):
+    def reverse_ode(self, xt, T=-1, save_states=False, save_dir="ode_state", **kwargs):
+        """Probability-flow Euler loop (:263-280): model forward + ONE fused update per step.  The reference does not
+        forward model kwargs here (:267); they are accepted so a conditioned network can be sampled this way too."""
         T = self.sample_T if T < 0 else T
+        xt = _require_cuda_f32("xt", xt)
+        if T == 0 or xt.numel() == 0:
+            return xt.clone()
+        if (self.use_cuda_graph and not save_states and hasattr(self.model, "forward_into")
+                and set(kwargs) == {"image_context"} and torch.is_tensor(self.mu)):
+            return self._reverse_sde_graph(xt, T, kwargs, ode=True)
         x = xt.clone()
+        fast_model = hasattr(self.model, "forward_into") and set(kwargs) <= {"image_context"}
         for t in reversed(range(1, T + 1)):
-            score = self.score_fn(x, t, self.sample_scale)
-            x = self.reverse_ode_step(x, score, t)
+            if fast_model:
+                noise = self.model.forward_into(x, self._mu_tensor(x), t * self.sample_scale, kwargs.get("image_context"))
+            else:
+                noise = self.model(x, self.mu, t * self.sample_scale, **kwargs)
+            x = self._fused_step(x, noise, t, is_score=False, with_noise=False, out=x, ode=True)
             if save_states:
                 interval = self.T // 100
                 if t % interval == 0:
                     self._save_state(x, save_dir, f"state_{t // interval}.png", dim=3)
+        _lib.watchdog()
         return x
 
     def ode_sampler(self, xt, rtol=1e-5, atol=1e-5, method="RK45", eps=1e-3):

@@ -8,6 +8,8 @@
                        pre-drawn Gaussians replacing ``torch.randn_like`` and the analytic
                        model ``get_real_noise`` (reference: :244-261), plus a single
                        ``reverse_sde_step`` and ``generate_random_states`` / ``noise_state``.
+* irsde_ode.npz     -- the reference's ``reverse_ode`` / ``reverse_ode_step`` (:48-49, :263-280) on the same
+                       inputs (`--ode-only` regenerates just this file).
 * unet_oracle.npz   -- output of oracle/unet_oracle.py (seed-1 weights) on a fixed input.
                        The reference ships no network source, so this one pins the oracle to
                        itself only (see the module header).
@@ -106,6 +108,28 @@ def gen_loop(IRSDE):
           xT.double().sum().item(), x_end.double().sum().item())
 
 
+def gen_ode(IRSDE):
+    """irsde_ode.npz -- the reference's own ``reverse_ode`` (:263-280) on the KAT-3 inputs with the analytic model,
+    every intermediate state, plus one isolated ``reverse_ode_step`` (:48-49)."""
+    loop = np.load(os.path.join(OUT, "irsde_loop.npz"))
+    mu, x0t, xT = (torch.from_numpy(loop[k]) for k in ("mu", "x0t", "xT"))
+    sde = IRSDE(max_sigma=0.4, T=100, schedule="cosine", eps=0.01, device="cpu")
+    sde.set_mu(mu)
+    sde.set_model(lambda x, m, t, **kw: sde.get_real_noise(x, x0t, int(t)))
+    states = []
+    x = xT.clone()
+    for t in reversed(range(1, 101)):
+        x = sde.reverse_ode_step(x, sde.score_fn(x, t, sde.sample_scale), t)
+        states.append(x.clone())
+    x_end = sde.reverse_ode(xT, T=-1)
+    assert torch.equal(x_end, states[-1])
+    eps_any = torch.from_numpy(loop["step_eps"])
+    x_step = sde.reverse_ode_step(xT, sde.get_score_from_noise(eps_any, 63), 63)
+    np.savez_compressed(os.path.join(OUT, "irsde_ode.npz"), states=torch.stack(states).numpy(), x_end=x_end.numpy(),
+                        step_out=x_step.numpy())
+    print("ODE sums:", x_end.double().sum().item(), x_step.double().sum().item())
+
+
 def gen_unet():
     sys.path.insert(0, ROOT)
     from oracle.unet_oracle import make_oracle_unet
@@ -124,7 +148,10 @@ def gen_unet():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     IRSDE = import_reference_irsde()
-    gen_tables(IRSDE)
-    gen_loop(IRSDE)
-    gen_unet()
+    if "--ode-only" not in sys.argv:
+        gen_tables(IRSDE)
+    if "--ode-only" not in sys.argv:
+        gen_loop(IRSDE)
+        gen_unet()
+    gen_ode(IRSDE)
     print("wrote", sorted(os.listdir(OUT)))

@@ -218,3 +218,49 @@ def test_sde_step_with_device_side_rng_parameters(n, offset):
         _lib.check(_lib.lib().idiff_sde_step_rng(got.data_ptr(), x.data_ptr(), e.data_ptr(), mu.data_ptr(), row.data_ptr(),
                                                  0, rng.data_ptr(), promise, n, s), "sde_step_rng")
         assert torch.equal(got, want)
+
+
+@pytest.fixture(scope="module")
+def ode(golden_dir):
+    return np.load(os.path.join(golden_dir, "irsde_ode.npz"))
+
+
+def test_ode_step_bit_exact_vs_reference_golden_and_oracle(loop, ode):
+    """SDE.reverse_ode_step (:48-49) with IRSDE.ode_reverse_drift (:181-182): the fused kernel's ODE mode."""
+    sde = _sde()
+    mu = torch.from_numpy(loop["mu"]).cuda()
+    sde.set_mu(mu)
+    t = int(loop["step_t"])
+    x = torch.from_numpy(loop["xT"]).cuda()
+    eps = torch.from_numpy(loop["step_eps"]).cuda()
+    out = sde.reverse_ode_step(x, sde.get_score_from_noise(eps, t), t)       # reference call shape
+    assert torch.equal(out.cpu(), torch.from_numpy(ode["step_out"])), (out.cpu() - torch.from_numpy(ode["step_out"])).abs().max()
+    s = O.make_schedule(0.4, 100, schedule="cosine", eps=0.01)
+    g = torch.Generator().manual_seed(77)
+    for shape, tt in [((3, 1, 17, 13), 100), ((2, 1, 64, 64), 1), ((1, 1, 1, 1), 42)]:
+        xx, ee, mm = (torch.randn(shape, generator=g) for _ in range(3))
+        ref = O.reverse_ode_step(s, xx, mm, ee, tt)
+        sde.set_mu(mm.cuda())
+        got = sde._fused_step(xx.cuda(), ee.cuda(), tt, is_score=False, with_noise=False, ode=True)
+        assert torch.equal(got.cpu(), ref), (shape, tt)
+
+
+def test_ode_loop_teacher_forced_bit_exact_and_free_running(loop, ode):
+    """Every one of the reference's 100 ODE states is reproduced bit for bit when the step starts from the
+    reference's previous state with the reference's eps (computed by the CPU oracle); the free-running fused loop
+    (`reverse_ode`, model = analytic get_real_noise as torch CUDA ops) stays within 2e-5."""
+    sde = _sde()
+    s = O.make_schedule(0.4, 100, schedule="cosine", eps=0.01)
+    mu_c, x0_c = torch.from_numpy(loop["mu"]), torch.from_numpy(loop["x0t"])
+    states = torch.from_numpy(ode["states"])
+    prev = torch.from_numpy(loop["xT"])
+    sde.set_mu(mu_c.cuda())
+    for i, t in enumerate(reversed(range(1, 101))):
+        eps = O.real_noise(s, prev, x0_c, mu_c, t)
+        got = sde._fused_step(prev.cuda(), eps.cuda(), t, is_score=False, with_noise=False, ode=True)
+        assert torch.equal(got.cpu(), states[i]), f"t={t}"
+        prev = states[i]
+    x0t = x0_c.cuda()
+    sde.set_model(lambda x, m, t, **kw: sde.get_real_noise(x, x0t, int(t)))
+    x_end = sde.reverse_ode(torch.from_numpy(loop["xT"]).cuda(), T=-1)
+    assert (x_end.cpu() - torch.from_numpy(ode["x_end"])).abs().max().item() < 2e-5

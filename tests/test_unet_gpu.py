@@ -337,3 +337,27 @@ def test_driver_protocol_with_checkpoint_round_trip(nets, tmp_path):
     # save() writes the reference's file names and the file loads back
     model.save(77, str(tmp_path / "out"))
     assert sorted(p.name for p in (tmp_path / "out").iterdir()) == ["77_NN.pth"]
+
+
+def test_reverse_ode_with_the_unet_graph_equals_eager_and_tracks_the_oracle(nets):
+    """Probability-flow sampler (utils/sde_utils.py:263-280) through the captured graph: bit-identical to the eager
+    loop, and within the per-step gate of the fp32 oracle network + oracle ODE loop."""
+    from instancediff_b200 import IRSDE
+    oracle, net = nets
+    B, H, W, T = 2, 32, 32, 8
+    x, mu, ctx = _inputs(B, H, W, seed=31)
+    outs = []
+    for use_graph in (True, False):
+        sde = IRSDE(0.4, T=100, schedule="cosine", eps=0.01, device=torch.device("cuda"))
+        sde.set_model(net)
+        sde.set_mu(mu)
+        sde.use_cuda_graph = use_graph
+        outs.append(sde.reverse_ode(x, T=T, image_context=ctx))
+        outs.append(sde.reverse_ode(x, T=T, image_context=ctx))            # second call: replay of the cached graph
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    s = O.make_schedule(0.4, 100, schedule="cosine", eps=0.01)
+    s = O.Schedule(s.T, s.max_sigma, s.sample_T, s.sample_scale, s.dt, s.thetas.cuda(), s.sigmas.cuda(),
+                   s.thetas_cumsum.cuda(), s.sigma_bars.cuda())
+    with torch.no_grad():
+        ref = O.reverse_ode(s, oracle, x, mu, T=T, image_context=ctx)
+    assert rel_err(outs[0], ref) <= 1e-2, describe(outs[0], ref, "reverse_ode")

@@ -26,3 +26,10 @@ x = sde.noise_state(mu)
 x = sde.reverse_sde(x, T=STEPS, image_context=ctx)
 torch.cuda.synchronize()
 print("ok", float(x.abs().mean()))
+# training-side state sampler: one fused launch, captured with `-k regex:random_states`
+sde.noise_source = "philox"
+ts = torch.randint(1, 101, (B, 1, 1, 1), generator=g)
+for _ in range(3):
+    _, xt = sde.generate_random_states(x, mu, timesteps=ts)
+torch.cuda.synchronize()
+print("random_states ok", float(xt.abs().mean()))
