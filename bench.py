@@ -288,42 +288,56 @@ def run_cuda(args):
     conv_tflops = conv["flops"] / (conv["ms"] / 1e3) / 1e12
     # fused SDE step, timed alone with events (16 B/element with the in-kernel Philox draw)
     n_el = xT.numel()
-    eps_buf = torch.randn_like(xT)
     row = sde._coef_table(dev)[50]
     s_ptr = torch.cuda.current_stream(dev).cuda_stream
-    xs = xT.clone()
 
-    def sde_launch():
-        _lib.check(_lib.lib().idiff_sde_step(xs.data_ptr(), xs.data_ptr(), eps_buf.data_ptr(), mu_d.data_ptr(), None,
-                                             row.data_ptr(), 0, 1, 1, 0, n_el, s_ptr), "sde_step")
-    for _ in range(5):
-        sde_launch()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(50):
-        sde_launch()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    sde_us = e0.elapsed_time(e1) / 50 * 1e3
+    def time_sde(n, nsets, reps):
+        """(us per launch inside a captured graph of 20 launches -- how the sampling loop runs it --, us per launch of
+        `reps` eager back-to-back launches, which adds the host-side launch path).  Launches rotate over `nsets`
+        buffer sets (x, eps, mu) so that one cycle moves more bytes than the 126 MB L2 holds: every launch reads
+        its inputs from HBM, as in the loop, where 2 GB of activations pass through L2 between two updates."""
+        sets = [tuple(torch.randn(n, device=dev) for _ in range(3)) for _ in range(nsets)]
+
+        def launch(stream, i):
+            xs_, eps_, mu_ = sets[i % nsets]
+            _lib.check(_lib.lib().idiff_sde_step(xs_.data_ptr(), xs_.data_ptr(), eps_.data_ptr(), mu_.data_ptr(), None,
+                                                 row.data_ptr(), 0, 1, 1, 0, n, stream), "sde_step")
+        for i in range(nsets):
+            launch(s_ptr, i)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        gr = torch.cuda.CUDAGraph()
+        nl = 20 if 20 % nsets == 0 else 2 * nsets
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(gr, stream=side):
+                for i in range(nl):
+                    launch(side.cuda_stream, i)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for _ in range(2):
+            gr.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        us_graph = e0.elapsed_time(e1) / (10 * nl) * 1e3
+        e0.record()
+        for i in range(reps):
+            launch(s_ptr, i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        del gr, sets
+        return us_graph, e0.elapsed_time(e1) / reps * 1e3
+
+    # 16 B per element per launch; rotate over enough sets that a cycle exceeds 2 x L2
+    sde_sets = max(2, -(-(2 * 126 * 1024 * 1024) // (16 * n_el)))
+    sde_us, sde_us_eager = time_sde(n_el, sde_sets, 48)
     sde_gbs = 16.0 * n_el / (sde_us * 1e-6) / 1e9
-    # The B=32 state (4 x 8.4 MB) is an 8 us launch that lives in the 126 MB L2.  The same kernel on the B=256 state of
-    # BASELINE config 3 (268 MB of traffic per launch, larger than L2) shows what it reaches against HBM.
+    # the same kernel on the B=256 state of BASELINE config 3 (268 MB of traffic per launch)
     n_big = 8 * n_el
-    xb, eb, mb = (torch.randn(n_big, device=dev) for _ in range(3))
-
-    def sde_big():
-        _lib.check(_lib.lib().idiff_sde_step(xb.data_ptr(), xb.data_ptr(), eb.data_ptr(), mb.data_ptr(), None,
-                                             row.data_ptr(), 0, 1, 1, 0, n_big, s_ptr), "sde_step")
-    for _ in range(3):
-        sde_big()
-    e0.record()
-    for _ in range(20):
-        sde_big()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    sde_big_us = e0.elapsed_time(e1) / 20 * 1e3
+    sde_big_us, sde_big_us_eager = time_sde(n_big, 2, 20)
     sde_big_gbs = 16.0 * n_big / (sde_big_us * 1e-6) / 1e9
-    del xb, eb, mb
 
     # DRAM bytes of the conv_gemm launches of one forward from the committed ncu capture of this configuration
     # (profiles/r01s2_final_conv_gemm_dram_bytes_ncu.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch)
@@ -369,8 +383,10 @@ def run_cuda(args):
                                 "tflops": split["1x1"]["flops"] / (split["1x1"]["ms"] / 1e3) / 1e12,
                                 "launches_per_forward": split["1x1"]["n"], "ms_per_forward": split["1x1"]["ms"]},
         "roofline_sde": {"bound": "hbm", "kernel": "sde_step_kernel", "achieved": sde_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                         "frac": sde_gbs / pk["hbm"], "us_per_launch": sde_us, "bytes_per_element": 16,
-                         "at_batch_256": {"elements": n_big, "us_per_launch": sde_big_us, "achieved": sde_big_gbs,
+                         "frac": sde_gbs / pk["hbm"], "us_per_launch": sde_us, "us_per_launch_eager": sde_us_eager,
+                         "bytes_per_element": 16, "timing": f"CUDA events around 10 replays of a captured graph of launches rotating over {sde_sets} buffer sets "
+                         "(one cycle > 2x the 126 MB L2, inputs come from HBM as in the loop); the eager figure adds the host launch path",
+                         "at_batch_256": {"elements": n_big, "us_per_launch": sde_big_us, "us_per_launch_eager": sde_big_us_eager, "achieved": sde_big_gbs,
                                           "frac": sde_big_gbs / pk["hbm"],
                                           "note": "same kernel on the B=256 state (268 MB per launch, exceeds L2)"}},
         "forward_breakdown_ms": {k: round(v["ms"], 4) for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1]["ms"])},

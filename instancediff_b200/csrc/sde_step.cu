@@ -63,8 +63,8 @@ IDIFF_DEVINL float sde_update(float x, float e, float mu, float z, const StepCoe
   return out;
 }
 
-template <bool kVec>
-__global__ void __launch_bounds__(256)
+template <bool kVec, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks)
 sde_step_kernel(float* __restrict__ xo, const float* __restrict__ x, const float* __restrict__ eps,
                 const float* __restrict__ mu, const float* __restrict__ z, const float* __restrict__ coef,
                 int is_score, int philox, uint64_t seed, uint64_t elem_offset, const uint64_t* __restrict__ rng_dev,
@@ -245,15 +245,22 @@ static int sde_step_launch(float* x_out, const float* x, const float* eps, const
   const bool vec = (n % 4 == 0) && aligned16(x_out) && aligned16(x) && aligned16(eps) && (!mu || aligned16(mu)) &&
                    (!z || aligned16(z)) && offset_mult4;
   if (vec) {
-    // exactly two float4 items per thread when the tensor is large enough: one balanced wave (<= 8 CTAs per SM)
+    // ONE resident wave: 4 CTAs per SM (the launch bound caps the kernel at 64 registers), every thread walks the
+    // tensor with the grid stride, two float4 items in flight per trip.  Measured inside a captured graph with inputs
+    // coming from HBM (tools/sweep_sde.py rotates buffer sets past the L2 size; B200, 16 B per element):
+    //   elements        one CTA per 512 items, <= 8 per SM (76 reg: 3 resident)    one wave of 4 CTAs per SM
+    //   2.1M  (B = 32)        7.69 us  4.36 TB/s                                    7.19 us  4.66 TB/s
+    //   4.2M  (B = 64)       13.93 us  4.82 TB/s                                   12.88 us  5.21 TB/s
+    //   16.8M (B = 256)      45.67 us  5.88 TB/s                                   42.85 us  6.26 TB/s
+    // 5 / 6 CTAs per SM (48 / 40 registers, spills) and a one-item software-pipelined loop were slower at every size.
     const size_t n4 = n / 4;
     size_t blocks = (n4 + 511) / 512;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > (size_t)148 * 4) blocks = (size_t)148 * 4;
     if (blocks < 1) blocks = 1;
-    sde_step_kernel<true><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+    sde_step_kernel<true, 4><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
         x_out, x, eps, mu, z, coef, input_is_score, use_philox, seed, elem_offset, rng_dev, n);
   } else {
-    sde_step_kernel<false><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+    sde_step_kernel<false, 1><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
         x_out, x, eps, mu, z, coef, input_is_score, use_philox, seed, elem_offset, rng_dev, n);
   }
   return check_launch("sde_step");

@@ -238,6 +238,12 @@ def test_testum_style_driver_end_to_end(tmp_path):
         assert len(files) == r["num"] and all(f.endswith("_672x224x1.raw") for f in files)
         trip = np.fromfile(str(tmp_path / "out" / name / files[0]), dtype=np.float32)
         assert trip.size == 224 * 672 and np.isfinite(trip).all()
+    # grouping items into one reverse process (--batch) changes the throughput, not the restored images
+    res2 = drv.run(flist, str(tmp_path / "out2"), NAMES[:2], max_items=2, T=4, batch=2)
+    for name in res:
+        assert res2[name]["RMSE"] == res[name]["RMSE"]
+        for f in os.listdir(tmp_path / "out" / name):
+            assert (tmp_path / "out" / name / f).read_bytes() == (tmp_path / "out2" / name / f).read_bytes()
 
 
 def test_empty_batch_and_zero_steps(nets):

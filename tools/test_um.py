@@ -22,7 +22,7 @@ from instancediff_b200 import data as D  # noqa: E402
 
 
 def run(flist, result_root, artifact_types, weights=None, max_items=1000000, T=-1, seed=1, device="cuda:0",
-        pth_dir=None, iter_label=None, use_ema=False):
+        pth_dir=None, iter_label=None, use_ema=False, batch=1):
     torch.manual_seed(seed)                                           # testUM.py:35-43
     np.random.seed(seed)
     dev = torch.device(device)
@@ -40,26 +40,41 @@ def run(flist, result_root, artifact_types, weights=None, max_items=1000000, T=-
     ds = D.SpeckleMedDataset(flist, phase="test", max_dataset_size=max_items, opt={"name": "test_b200"},
                              use_artifact_type=artifact_types)
     results = {}
-    with torch.no_grad():                                             # :109
-        for i in range(len(ds)):
-            item = ds[i]
-            LQ, GT = item["LQ"][None], item["GT"][None]               # [1,1,224,224], inputs in [-1, 1]
-            model.feed_data({"input": LQ.to(dev), "target": GT.to(dev), "names": [item["name"]],
-                             "A_emb": item["A_emb"][None].to(dev)})   # :128-139
-            tic = time.time()
-            model.test()                                              # :142 (result lands on the host: synchronises)
-            toc = time.time()
-            visuals = model.get_visuals()                             # :146
-            pred = D.to_unit_range(visuals)                           # :151-152
-            target = D.to_unit_range(GT.numpy())
+
+    def flush(group):
+        """One reverse process for a group of items (testUM.py runs batch_size 1; a group of N items is the same
+        computation per item -- every sample draws from its own Philox stream, indexed by its position in the data
+        set, so the restored images do not depend on the grouping)."""
+        LQ = torch.stack([it["LQ"] for _, it in group])               # [N,1,224,224], inputs in [-1, 1]
+        GT = torch.stack([it["GT"] for _, it in group])
+        model.feed_data({"input": LQ.to(dev), "target": GT.to(dev), "names": [it["name"] for _, it in group],
+                         "A_emb": torch.stack([it["A_emb"] for _, it in group]).to(dev)})   # :128-139
+        tic = time.time()
+        model.test()                                                  # :142 (result lands on the host: synchronises)
+        toc = time.time()
+        visuals = model.get_visuals()                                 # :146
+        for k, (i, item) in enumerate(group):
+            pred = D.to_unit_range(visuals[k:k + 1])                  # :151-152
+            target = D.to_unit_range(GT[k:k + 1].numpy())
             rmse, psnr = D.rmse_psnr(pred, target)
-            path = D.save_triptych(item["LQ"], torch.from_numpy(visuals), item["GT"], result_root, item["name"], i)
+            path = D.save_triptych(item["LQ"], torch.from_numpy(visuals[k]), item["GT"], result_root, item["name"], i)
             r = results.setdefault(item["name"], dict(num=0, RMSE=[], PSNR=[], time=[]))
             r["num"] += 1
             r["RMSE"].append(rmse)
             r["PSNR"].append(psnr)
-            r["time"].append(toc - tic)
-            print(f" Testing {i}, {item['GT_path']}: RMSE={rmse:.5f}, PSNR={psnr:.3f}, {toc - tic:.2f} s -> {path}")
+            r["time"].append((toc - tic) / len(group))
+            print(f" Testing {i}, {item['GT_path']}: RMSE={rmse:.5f}, PSNR={psnr:.3f}, {(toc - tic) / len(group):.3f} s/image "
+                  f"(group of {len(group)}) -> {path}")
+
+    with torch.no_grad():                                             # :109
+        group = []
+        for i in range(len(ds)):
+            group.append((i, ds[i]))
+            if len(group) == max(1, batch):
+                flush(group)
+                group = []
+        if group:
+            flush(group)
     for name, r in results.items():
         print(f"{name}: n={r['num']} RMSE={np.mean(r['RMSE']):.5f} PSNR={np.mean(r['PSNR']):.3f} "
               f"mean time {np.mean(r['time']):.2f} s")
@@ -77,16 +92,18 @@ def main():
     ap.add_argument("--artifact-type", nargs="*", default=None)
     ap.add_argument("--max-items", type=int, default=1000000)
     ap.add_argument("--T", type=int, default=-1)
+    ap.add_argument("--batch", type=int, default=1, help="items restored per reverse process (testUM.py: 1); the "
+                    "results do not depend on it, the throughput does")
     args = ap.parse_args()
     tmp = None
     if args.flist is None:
         tmp = tempfile.TemporaryDirectory()
         args.flist = D.make_synthetic_dataset(tmp.name)
         args.artifact_type = args.artifact_type or D.MODALITY_NAMES[:2]
-        args.max_items = min(args.max_items, 2)
+        args.max_items = min(args.max_items, 6)
     root = args.result_root or os.path.join(tempfile.gettempdir(), "idiff_results")
     run(args.flist, root, args.artifact_type or [], args.weights, args.max_items, args.T, pth_dir=args.pth_dir,
-        iter_label=args.iter, use_ema=args.use_ema)
+        iter_label=args.iter, use_ema=args.use_ema, batch=args.batch)
 
 
 if __name__ == "__main__":
