@@ -361,7 +361,7 @@ class IRSDE(SDE):
         # the Philox stream {seed, offset} lives in device memory, so the captured graph does not depend on it:
         # a data-set loop (one reverse process per item, each with its own offset) replays ONE graph
         off4 = int(self.philox_offset) % 4 == 0
-        key = (tuple(xt.shape), id(self.model), str(dev), off4, ode)
+        key = (tuple(xt.shape), id(self.model), getattr(self.model, "_version", 0), str(dev), off4, ode)
         st = self._graph_cache.pop(key, None)
         L = _lib.lib()
         if st is None:
@@ -369,7 +369,8 @@ class IRSDE(SDE):
                       counter=torch.zeros(1, dtype=torch.int32, device=dev),
                       row=torch.zeros(8, dtype=torch.float32, device=dev),
                       time=torch.zeros(1, dtype=torch.float32, device=dev),
-                      rng=torch.zeros(2, dtype=torch.int64, device=dev), graph=None)
+                      rng=torch.zeros(2, dtype=torch.int64, device=dev), graph=None,
+                      model=self.model)                 # keeps id(model) in the key unique while the entry lives
             while len(self._graph_cache) >= self.graph_cache_size:      # oldest entry first (dicts keep order)
                 self._graph_cache.pop(next(iter(self._graph_cache)))
         self._graph_cache[key] = st                                     # most recently used last

@@ -180,9 +180,17 @@ class ConditionalUNet:
         return self
 
     def to(self, device):
-        if torch.device(device) != self.device:
+        def norm(d):
+            d = torch.device(d)
+            if d.type == "cuda" and d.index is None:
+                return torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+            return d
+        if norm(device) != norm(self.device):
             self.device = torch.device(device)
             self.params = {k: v.to(self.device) for k, v in self.params.items()}
+            self._plans.clear()                      # launch plans, workspaces and context vectors live on the old device
+            self._crossvec.clear()
+            self._ctx_key = self._ctx_ref = None
             self._pack()
         return self
 
@@ -288,6 +296,7 @@ class ConditionalUNet:
         self.pk = pk
         self._plans.clear()
         self._ctx_key = None
+        self._version = getattr(self, "_version", 0) + 1     # captured graphs hold pointers into the old packing
 
     # ------------------------------------------------------------------ conditioning
     def spatial_layers(self):

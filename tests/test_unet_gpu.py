@@ -367,3 +367,30 @@ def test_reverse_ode_with_the_unet_graph_equals_eager_and_tracks_the_oracle(nets
     with torch.no_grad():
         ref = O.reverse_ode(s, oracle, x, mu, T=T, image_context=ctx)
     assert rel_err(outs[0], ref) <= 1e-2, describe(outs[0], ref, "reverse_ode")
+
+
+def test_reloading_weights_invalidates_the_captured_loop(nets):
+    """A graph captured before `load_state_dict` points into the old weight packing; the next call must re-capture
+    and follow the new weights (and `to()` of an equivalent device spelling must not re-pack)."""
+    from instancediff_b200 import ConditionalUNet, IRSDE
+    oracle, _ = nets
+    net = ConditionalUNet(device="cuda", seed=5)
+    x, mu, ctx = _inputs(1, 32, 32, seed=2)
+    sde = IRSDE(0.4, T=100, schedule="cosine", eps=0.01, device=torch.device("cuda"))
+    sde.set_model(net)
+    sde.set_mu(mu)
+    sde.noise_source, sde.philox_seed = "philox", 3
+    a = sde.reverse_sde(x, T=4, image_context=ctx)
+    v = net._version
+    net.to(torch.device("cuda:0"))
+    assert net._version == v                                   # same device, nothing rebuilt
+    assert torch.equal(sde.reverse_sde(x, T=4, image_context=ctx), a)
+    net.load_state_dict(oracle.state_dict())
+    assert net._version == v + 1
+    b = sde.reverse_sde(x, T=4, image_context=ctx)
+    sde2 = IRSDE(0.4, T=100, schedule="cosine", eps=0.01, device=torch.device("cuda"))
+    sde2.set_model(nets[1])
+    sde2.set_mu(mu)
+    sde2.noise_source, sde2.philox_seed = "philox", 3
+    assert torch.equal(b, sde2.reverse_sde(x, T=4, image_context=ctx))
+    assert not torch.equal(a, b)
