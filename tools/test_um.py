@@ -19,6 +19,7 @@ import torch  # noqa: E402
 
 from instancediff_b200 import create_model, create_sde  # noqa: E402
 from instancediff_b200 import data as D  # noqa: E402
+from instancediff_b200.metrics import ssim_unit_range  # noqa: E402
 
 
 def run(flist, result_root, artifact_types, weights=None, max_items=1000000, T=-1, seed=1, device="cuda:0",
@@ -57,13 +58,15 @@ def run(flist, result_root, artifact_types, weights=None, max_items=1000000, T=-
             pred = D.to_unit_range(visuals[k:k + 1])                  # :151-152
             target = D.to_unit_range(GT[k:k + 1].numpy())
             rmse, psnr = D.rmse_psnr(pred, target)
+            ssim = ssim_unit_range(pred, target)                      # :158-161
             path = D.save_triptych(item["LQ"], torch.from_numpy(visuals[k]), item["GT"], result_root, item["name"], i)
-            r = results.setdefault(item["name"], dict(num=0, RMSE=[], PSNR=[], time=[]))
+            r = results.setdefault(item["name"], dict(num=0, RMSE=[], SSIM=[], PSNR=[], time=[]))
             r["num"] += 1
             r["RMSE"].append(rmse)
             r["PSNR"].append(psnr)
+            r["SSIM"].append(ssim)
             r["time"].append((toc - tic) / len(group))
-            print(f" Testing {i}, {item['GT_path']}: RMSE={rmse:.5f}, PSNR={psnr:.3f}, {(toc - tic) / len(group):.3f} s/image "
+            print(f" Testing {i}, {item['GT_path']}: RMSE={rmse:.5f}, SSIM={ssim:.4f}, PSNR={psnr:.3f}, {(toc - tic) / len(group):.3f} s/image "
                   f"(group of {len(group)}) -> {path}")
 
     with torch.no_grad():                                             # :109
@@ -76,7 +79,7 @@ def run(flist, result_root, artifact_types, weights=None, max_items=1000000, T=-
         if group:
             flush(group)
     for name, r in results.items():
-        print(f"{name}: n={r['num']} RMSE={np.mean(r['RMSE']):.5f} PSNR={np.mean(r['PSNR']):.3f} "
+        print(f"{name}: n={r['num']} RMSE={np.mean(r['RMSE']):.5f} SSIM={np.mean(r['SSIM']):.4f} PSNR={np.mean(r['PSNR']):.3f} "
               f"mean time {np.mean(r['time']):.2f} s")
     return results
 
