@@ -8,6 +8,8 @@ fixtures produced by importing the reference's own ``SpeckleMedDataset`` (``orac
 from __future__ import annotations
 
 import json
+import logging
+import math
 import os
 import platform
 from typing import Dict, List, Sequence
@@ -70,6 +72,65 @@ def create_SpeckleMedDataset(params=None):
     dataset_file = params["dataset_file_win"] if platform.system() == "Windows" else params["dataset_file"]
     return SpeckleMedDataset(dataset_file, phase=params["name"].split("_")[0], max_dataset_size=params["max_dataset_size"],
                              opt=params, use_artifact_type=params["use_artifact_type"])
+
+
+def create_dataset(dataset_opt):
+    """``data/__init__.py:37-52``: factory keyed by ``dataset_opt['mode']``; only ``SpeckleMed`` exists upstream."""
+    mode = dataset_opt["mode"]
+    if mode != "SpeckleMed":
+        raise NotImplementedError("Dataset [{:s}] is not recognized.".format(mode))
+    dataset = create_SpeckleMedDataset(dataset_opt)
+    logging.getLogger("base").info("Dataset [{:s} - {:s}] is created.".format(dataset.__class__.__name__, dataset_opt["name"]))
+    return dataset
+
+
+def create_dataloader(dataset, dataset_opt, opt=None, sampler=None):
+    """``data/__init__.py:8-34``.  train: per-rank batch ``batch_size // world_size`` without shuffling when
+    ``opt['dist']`` (the sampler shuffles), else the full batch shuffled with ``n_workers * len(gpu_ids)`` workers;
+    ``drop_last`` and pinned memory.  Any other phase: batch 1, in order, no workers, pinned only for ``val``."""
+    phase = dataset_opt["phase"]
+    if phase == "train":
+        if opt["dist"]:
+            world_size = torch.distributed.get_world_size()
+            num_workers = dataset_opt["n_workers"]
+            assert dataset_opt["batch_size"] % world_size == 0
+            batch_size, shuffle = dataset_opt["batch_size"] // world_size, False
+        else:
+            num_workers = dataset_opt["n_workers"] * len(opt["gpu_ids"])
+            batch_size, shuffle = dataset_opt["batch_size"], True
+        return data.DataLoader(dataset, batch_size=batch_size, shuffle=shuffle, num_workers=num_workers, sampler=sampler,
+                               drop_last=True, pin_memory=True)
+    return data.DataLoader(dataset, batch_size=1, shuffle=False, num_workers=0, pin_memory=(phase == "val"))
+
+
+class DistIterSampler(data.Sampler):
+    """``data/data_sampler.py:13-67``: the data set enlarged ``ratio`` times for iteration-oriented training.  Each
+    epoch draws ONE permutation of ``num_samples * num_replicas`` virtual indices from a generator seeded with the
+    epoch number, folds it onto the data set with a modulo and gives rank r every ``num_replicas``-th entry from r."""
+
+    def __init__(self, dataset, num_replicas=None, rank=None, ratio=100):
+        if num_replicas is None or rank is None:
+            if not torch.distributed.is_available():
+                raise RuntimeError("Requires distributed package to be available")
+            num_replicas = torch.distributed.get_world_size() if num_replicas is None else num_replicas
+            rank = torch.distributed.get_rank() if rank is None else rank
+        self.dataset, self.num_replicas, self.rank, self.epoch = dataset, num_replicas, rank, 0
+        self.num_samples = int(math.ceil(len(dataset) * ratio / num_replicas))
+        self.total_size = self.num_samples * num_replicas
+
+    def __iter__(self):
+        gen = torch.Generator()
+        gen.manual_seed(self.epoch)
+        n = len(self.dataset)
+        mine = (torch.randperm(self.total_size, generator=gen)[self.rank:self.total_size:self.num_replicas] % n).tolist()
+        assert len(mine) == self.num_samples
+        return iter(mine)
+
+    def __len__(self):
+        return self.num_samples
+
+    def set_epoch(self, epoch):
+        self.epoch = epoch
 
 
 # ---- result side (testUM.py:144-173) -----------------------------------------------------------------------
