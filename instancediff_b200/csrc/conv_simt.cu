@@ -66,15 +66,25 @@ stem_conv7_kernel(const float* __restrict__ x, const float* __restrict__ mu, con
 constexpr int HT = 16, HP = HT + 2;
 
 // ---- head on tensor cores: 3x3, 64 -> 1, fp32 out ---------------------------------------------------------
-// The CUDA-core version of this layer issued 1700 instructions per pixel (576 FMAs + 570 bf16 unpacks + 216 LDS.128) and
-// ran at 1.4 TB/s.  Here a warp computes 16 pixels of a row with mma.sync.m16n8k16 (bf16 -> fp32): A = 16 pixels x
-// 16 channels straight out of the shared-memory patch (ldmatrix.x4), B = 16 channels x 8 columns of which column 0
-// holds bf16(w) and column 1 holds bf16(w - bf16(w)) (the weights keep ~16 mantissa bits; eps feeds the SDE
-// update directly), 36 MMAs per 16 pixels.  tcgen05 would spend a 64-cycle M128 slot per K=16 step on an N=8
-// problem; the legacy warp-level MMA is the right size for this 0.04 %-of-FLOPs layer.
+// The CUDA-core version of this layer issued 1700 instructions per pixel and ran at 1.4 TB/s; the first mma.sync version
+// multiplied every output pixel's 9 shifted patch views (36 ldmatrix.x4 + 36 MMAs per 16 pixels, 1152 B of shared-
+// memory reads per pixel, L1 85 % busy: profiles/r01s2 head_conv3 capture).  A 1-channel convolution is 9 dot products
+// per INPUT pixel followed by a 9-point gather, so the taps go on the N side instead:
+//   phase A  partial[p][tap] = w_tap . x[p] for every pixel p of the 18 x 18 patch: the patch is a linear array of
+//            pixels, a warp takes 16 consecutive ones (ldmatrix.x4, ONE A fragment per 16 channels) and multiplies them
+//            with three n8 tiles whose columns are (tap, hi) / (tap, lo) pairs -- bf16(w) and bf16(w - bf16(w)): the
+//            weights keep ~16 mantissa bits because eps feeds the SDE update directly.  4 ldmatrix + 12 MMAs per 16
+//            pixels, 128 B of shared-memory reads per pixel.
+//   phase B  out[y][x] = bias + sum_tap partial[(y+dy, x+dx)][tap]: 9 fp32 reads per output pixel, one thread each.
+// tcgen05 would spend a 64-cycle M128 slot per K=16 step on an N=24 problem; the warp-level MMA is the right size
+// for this 0.04 %-of-FLOPs layer.
 constexpr int HM_PITCH = 64 * 2 + 16;                              // bytes per patch pixel (ldmatrix rows: conflict-free)
-constexpr int HM_WFRAG = 36 * 32 * 8;                              // [tap*4 + kchunk][lane] -> (b0, b1)
-constexpr int HM_SMEM = HM_WFRAG + HP * HP * HM_PITCH;
+constexpr int HM_NPIX = HP * HP;                                   // 324
+constexpr int HM_MT = (HM_NPIX + 15) / 16;                         // 21 m16 tiles (the last one runs into 12 pad pixels)
+constexpr int HM_PIXPAD = HM_MT * 16;
+constexpr int HM_WFRAG = 3 * 4 * 32 * 8;                           // [n-tile][k-chunk][lane] -> (b0, b1)
+constexpr int HM_PP = 9;                                           // floats per pixel of the partial array (odd: banks)
+constexpr int HM_SMEM = HM_WFRAG + HM_PIXPAD * HM_PITCH + HM_PIXPAD * HM_PP * 4;
 
 __global__ void __launch_bounds__(256, 2)
 head_conv3_mma_kernel(const __nv_bfloat16* __restrict__ src, const uint4* __restrict__ wpk, float bias,
@@ -82,12 +92,14 @@ head_conv3_mma_kernel(const __nv_bfloat16* __restrict__ src, const uint4* __rest
   extern __shared__ __align__(16) uint8_t hsm[];
   uint2* wfrag = reinterpret_cast<uint2*>(hsm);
   uint8_t* patch = hsm + HM_WFRAG;
+  float* part = reinterpret_cast<float*>(hsm + HM_WFRAG + HM_PIXPAD * HM_PITCH);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // B fragments, pre-packed on the host (packing.py::pack_head_weight): lane holds k = 2*(lane%4) + {0,1} (b0) and
-  // k + 8 (b1) of column n = lane/4; column 0 = bf16(w), column 1 = bf16(w - bf16(w)), the rest zero
+  // k + 8 (b1) of column n = lane/4 of n-tile j; column n is tap 4j + n/2, bf16(w) for even n, bf16(w - bf16(w)) for odd
   for (int i = tid; i < HM_WFRAG / 16; i += 256) reinterpret_cast<uint4*>(wfrag)[i] = __ldg(wpk + i);
-  // Persistent CTA: the NEXT tile's patch (11 x 16 B per thread) is in flight while the current one is multiplied
-  // (one tile per CTA spent half of its life waiting for its own loads).
+  for (int i = tid; i < (HM_PIXPAD - HM_NPIX) * HM_PITCH / 16; i += 256)      // pad pixels: defined (never used) values
+    reinterpret_cast<uint4*>(patch + HM_NPIX * HM_PITCH)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // Persistent CTA: the NEXT tile's patch (11 x 16 B per thread) is in flight while the current one is multiplied.
   constexpr int VPP = 8, NL = (HP * HP * VPP + 255) / 256;
   uint4 q[NL];
   auto fetch = [&](int tile) {
@@ -104,12 +116,13 @@ head_conv3_mma_kernel(const __nv_bfloat16* __restrict__ src, const uint4* __rest
     }
   };
   const uint32_t patch_u = smem_u32(patch);
-  const int g = lane >> 2;
+  const int g = lane >> 2, qd = lane & 3;
+  const int oty = tid >> 4, otx = tid & 15;                 // phase B: this thread's output pixel of the 16 x 16 tile
   if ((int)blockIdx.x < total) fetch(blockIdx.x);
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     const int tx = tile % tiles_x, r = tile / tiles_x, ty0 = r % tiles_y, b = r / tiles_y;
     const int oy0 = ty0 * HT, ox0 = tx * HT;
-    __syncthreads();                                   // every warp is done with the previous patch
+    __syncthreads();                                   // every thread is done with the previous patch and partials
 #pragma unroll
     for (int k = 0; k < NL; ++k) {
       const int i = tid + 256 * k;
@@ -117,35 +130,48 @@ head_conv3_mma_kernel(const __nv_bfloat16* __restrict__ src, const uint4* __rest
     }
     __syncthreads();
     if (tile + (int)gridDim.x < total) fetch(tile + gridDim.x);
+    // ---- phase A: per-pixel tap partials ----
 #pragma unroll 1
-    for (int rr = 0; rr < 2; ++rr) {
-      const int ty = warp * 2 + rr;
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
-      // ldmatrix row of this lane: pixel (lane & 15) of the row, 8-channel block (lane >> 4)
-      const uint32_t a_lane = patch_u + (uint32_t)((ty * HP + (lane & 15)) * HM_PITCH + (lane >> 4) * 16);
+    for (int mt = warp; mt < HM_MT; mt += 8) {
+      float c[3][4];
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const uint32_t a_tap = a_lane + (uint32_t)(((tap / 3) * HP + (tap % 3)) * HM_PITCH);
+      for (int j = 0; j < 3; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+      // ldmatrix row of this lane: pixel (lane & 15) of the 16, 8-channel block (lane >> 4)
+      const uint32_t a_lane = patch_u + (uint32_t)((mt * 16 + (lane & 15)) * HM_PITCH + (lane >> 4) * 16);
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {
-          uint32_t a0, a1, a2, a3;
-          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(a_tap + kc * 32));
-          const uint2 bf = wfrag[(tap * 4 + kc) * 32 + lane];
+      for (int kc = 0; kc < 4; ++kc) {
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(a_lane + kc * 32));
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const uint2 bf = wfrag[(j * 4 + kc) * 32 + lane];
           asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
                        "{%0, %1, %2, %3};"
-                       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                       : "+f"(c[j][0]), "+f"(c[j][1]), "+f"(c[j][2]), "+f"(c[j][3])
                        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
         }
       }
-      if ((lane & 3) == 0) {                              // columns 0 (hi weights) and 1 (lo weights) of rows g, g + 8
-        const int oy = oy0 + ty;
-        if (oy < H) {
-          float* orow = out + ((size_t)b * H + oy) * W;
-          if (ox0 + g < W) orow[ox0 + g] = c[0] + c[1] + bias;
-          if (ox0 + g + 8 < W) orow[ox0 + g + 8] = c[2] + c[3] + bias;
+      // accumulator columns (2*qd, 2*qd + 1) of n-tile j = (hi, lo) of tap 4j + qd; rows g and g + 8
+      float* p0 = part + (mt * 16 + g) * HM_PP;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int tap = 4 * j + qd;
+        if (tap < 9) {
+          p0[tap] = c[j][0] + c[j][1];
+          p0[8 * HM_PP + tap] = c[j][2] + c[j][3];
         }
       }
+    }
+    __syncthreads();
+    // ---- phase B: 9-point gather ----
+    {
+      const float* pc = part + (oty * HP + otx) * HM_PP;
+      float acc = bias;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) acc += pc[((tap / 3) * HP + (tap % 3)) * HM_PP + tap];
+      const int oy = oy0 + oty, ox = ox0 + otx;
+      if (oy < H && ox < W) out[((size_t)b * H + oy) * W + ox] = acc;
     }
   }
 }
@@ -212,7 +238,7 @@ int idiff_head_conv3(const void* src, const void* w, float bias, float* out, int
     if (e != cudaSuccess) { num_sms = 0; return fail(IDIFF_ERR_CUDA, "head_conv3 setup: %s", cudaGetErrorString(e)); }
   }
   const int tiles_x = (W + HT - 1) / HT, tiles_y = (H + HT - 1) / HT, total = tiles_x * tiles_y * B;
-  const int grid = total < 2 * num_sms ? total : 2 * num_sms;       // 2 resident CTAs per SM (114 registers per thread)
+  const int grid = total < 2 * num_sms ? total : 2 * num_sms;       // 2 resident CTAs per SM
   head_conv3_mma_kernel<<<grid, 256, HM_SMEM, as_stream(stream)>>>((const __nv_bfloat16*)src, (const uint4*)w, bias, out, H, W,
                                                                    tiles_x, tiles_y, total);
   return check_launch("head_conv3");

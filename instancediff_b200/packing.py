@@ -80,20 +80,25 @@ def pack_stem_weight(w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
 
 def pack_head_weight(w: torch.Tensor) -> torch.Tensor:
     """Head 3x3 conv weights (w: [1, 64, 3, 3] or [3, 3, 64] fp32) -> the mma.sync.m16n8k16 B fragments
-    idiff_head_conv3 loads: [36 chunks = tap*4 + k-chunk][32 lanes][b0, b1] uint32, where lane holds
-    k = 2*(lane%4) + {0,1} (b0) and k + 8 (b1) of column n = lane//4; column 0 = bf16(w), column 1 = bf16(w - bf16(w))
-    (the fp32 weights keep ~16 mantissa bits), columns 2..7 zero.  Returned as a bf16 tensor of 4608 elements."""
+    idiff_head_conv3 loads: [3 n-tiles][4 k-chunks][32 lanes][b0, b1] uint32.  The taps sit on the N side: column
+    n = lane//4 of n-tile j is tap 4j + n//2, holding bf16(w) for even n and bf16(w - bf16(w)) for odd n (the fp32
+    weights keep ~16 mantissa bits); taps 9..11 are zero.  A lane holds k = 2*(lane%4) + {0,1} (b0) and k + 8 (b1) of
+    its column.  Returned as a bf16 tensor of 1536 elements."""
     if w.dim() == 4:
         w = w[0].permute(1, 2, 0)                                   # [3, 3, 64]
     wk = w.reshape(9, 4, 16).float()                                # [tap][k-chunk][k]
     hi = wk.to(torch.bfloat16)
     lo = (wk - hi.float()).to(torch.bfloat16)
-    frag = torch.zeros(9, 4, 32, 4, dtype=torch.bfloat16, device=w.device)      # [tap][kc][lane][b0.lo, b0.hi, b1.lo, b1.hi]
-    for lane in range(8):                                           # only columns n = 0 (lanes 0-3) and 1 (lanes 4-7)
-        src = hi if lane < 4 else lo
-        k0 = (lane % 4) * 2
-        frag[:, :, lane, 0] = src[:, :, k0]
-        frag[:, :, lane, 1] = src[:, :, k0 + 1]
-        frag[:, :, lane, 2] = src[:, :, k0 + 8]
-        frag[:, :, lane, 3] = src[:, :, k0 + 9]
+    frag = torch.zeros(3, 4, 32, 4, dtype=torch.bfloat16, device=w.device)      # [j][kc][lane][b0.lo, b0.hi, b1.lo, b1.hi]
+    for j in range(3):
+        for lane in range(32):
+            n, k0 = lane // 4, (lane % 4) * 2
+            tap = 4 * j + n // 2
+            if tap >= 9:
+                continue
+            src = hi if n % 2 == 0 else lo
+            frag[j, :, lane, 0] = src[tap, :, k0]
+            frag[j, :, lane, 1] = src[tap, :, k0 + 1]
+            frag[j, :, lane, 2] = src[tap, :, k0 + 8]
+            frag[j, :, lane, 3] = src[tap, :, k0 + 9]
     return frag.reshape(-1).contiguous()
