@@ -17,8 +17,9 @@ from .sampler import create_sde, gather_shards, sample_sharded, shard_bounds  # 
 from .model import RestorationModel, create_model  # noqa: F401
 from . import checkpoint  # noqa: F401
 from . import metrics  # noqa: F401
+from .parallel import GradientAllReducer  # noqa: F401
 from .metrics import calculate_psnr, calculate_ssim, tensor2img  # noqa: F401  (utils/__init__.py:3 exports them next to IRSDE)
 
 __all__ = ["IRSDE", "SDE", "ConditionalUNet", "param_specs", "create_sde", "sample_sharded", "shard_bounds", "gather_shards",
-           "RestorationModel", "create_model", "checkpoint", "metrics", "calculate_psnr", "calculate_ssim", "tensor2img",
+           "RestorationModel", "create_model", "checkpoint", "metrics", "GradientAllReducer", "calculate_psnr", "calculate_ssim", "tensor2img",
            "IdiffError", "LIB_PATH"]

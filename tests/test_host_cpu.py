@@ -175,3 +175,68 @@ def test_two_rank_gloo_gather_reassembles_batch_in_order():
     for p in procs:
         p.join(timeout=60)
     assert all(results) and all(p.exitcode == 0 for p in procs)
+
+
+def _allreduce_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from instancediff_b200.parallel import GradientAllReducer
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    ok = []
+
+    def make():
+        torch.manual_seed(0)                                      # identical replicas, as DDP starts them
+        return torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.SiLU(), torch.nn.Linear(16, 16), torch.nn.SiLU(),
+                                   torch.nn.Linear(16, 3))
+    xs = [torch.randn(5, 6, generator=torch.Generator().manual_seed(10 + r)) for r in range(world)]
+    # expected: average over ranks of the per-rank gradients, computed locally on every rank
+    want = None
+    for r in range(world):
+        m = make()
+        m(xs[r]).square().mean().backward()
+        g = [p.grad.clone() for p in m.parameters()]
+        want = g if want is None else [a + b for a, b in zip(want, g)]
+    want = [w / world for w in want]
+    # (a) hooks fire the buckets from inside backward; tiny buckets force several of them
+    net = make()
+    red = GradientAllReducer(net.parameters(), bucket_mb=0.0005).attach()
+    ok.append(len(red.buckets) > 2)
+    for _ in range(2):                                            # two steps: bucket state is re-armed by wait()
+        net.zero_grad(set_to_none=False)
+        net(xs[rank]).square().mean().backward()
+        red.wait()
+        ok.append(all(torch.allclose(p.grad, w, atol=1e-6) for p, w in zip(net.parameters(), want)))
+    red.detach()
+    # (b) manual mode, bf16 wire format, a parameter without a gradient counts as zeros
+    net2 = make()
+    net2(xs[rank]).square().mean().backward()
+    net2[4].bias.grad = None
+    red2 = GradientAllReducer(net2.parameters(), bucket_mb=25, comm_dtype=torch.bfloat16)
+    red2.reduce().wait()
+    ok.append(len(red2.buckets) == 1 and red2.bytes_per_step == 2 * sum(p.numel() for p in net2.parameters()))
+    ok.append(all(torch.allclose(p.grad, w, atol=2e-2, rtol=2e-2) for p, w in list(zip(net2.parameters(), want))[:-1]))
+    ok.append(bool((net2[4].bias.grad == 0).all()))
+    # every rank ends with the same bits
+    flat = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    ok.append(all(torch.equal(gathered[0], t) for t in gathered))
+    dist.barrier()
+    q.put(all(ok))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_allreduce_matches_ddp_averaging():
+    """Config 5's only collective (models/drift_noise_model.py:145-146 wraps the nets in DDP): bucketed, asynchronous,
+    launched from backward hooks; world size 2 on gloo."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(results) and all(p.exitcode == 0 for p in procs)
