@@ -240,3 +240,40 @@ def test_two_rank_gloo_gradient_allreduce_matches_ddp_averaging():
     for p in procs:
         p.join(timeout=60)
     assert all(results) and all(p.exitcode == 0 for p in procs)
+
+
+def test_head_weight_fragments_reproduce_the_convolution():
+    """packing.pack_head_weight lays the 3x3 x 64 -> 1 weights out as mma.sync.m16n8k16 B fragments with the taps on
+    the N side (csrc/conv_simt.cu).  Consuming them the way the kernel does -- per-pixel tap partials, then the
+    9-point gather -- must give the fp32 convolution (weights are split hi + lo: ~2^-16 relative)."""
+    from instancediff_b200.packing import pack_head_weight
+    g = torch.Generator().manual_seed(5)
+    w = (torch.rand(1, 64, 3, 3, generator=g) * 2 - 1) / 24
+    frag = pack_head_weight(w).float().reshape(3, 4, 32, 4)                 # [n-tile][k-chunk][lane][b0.lo b0.hi b1.lo b1.hi]
+    assert frag.numel() == 1536
+    # B[j][kc] as a 16 x 8 matrix: lane (n = lane // 4, q = lane % 4) holds k = 2q, 2q+1 (b0) and 2q+8, 2q+9 (b1) of column n
+    Bm = torch.zeros(3, 4, 16, 8)
+    for lane in range(32):
+        n, q = lane // 4, lane % 4
+        for slot, k in enumerate((2 * q, 2 * q + 1, 2 * q + 8, 2 * q + 9)):
+            Bm[:, :, k, n] = frag[:, :, lane, slot]
+    H, W = 7, 9
+    x = torch.randn(1, 64, H, W, generator=g).to(torch.bfloat16).float()
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1))[0].permute(1, 2, 0)       # [H+2][W+2][64] patch with halo
+    part = torch.zeros(H + 2, W + 2, 9)
+    for j in range(3):
+        acc = torch.zeros(H + 2, W + 2, 8)
+        for kc in range(4):
+            acc += xp[:, :, kc * 16:(kc + 1) * 16] @ Bm[j, kc]              # the m16n8k16 MMAs of n-tile j
+        for qd in range(4):
+            tap = 4 * j + qd
+            if tap < 9:
+                part[:, :, tap] = acc[:, :, 2 * qd] + acc[:, :, 2 * qd + 1]   # (hi, lo) column pair of the tap
+    out = torch.zeros(H, W)
+    for tap in range(9):
+        dy, dx = tap // 3, tap % 3
+        out += part[dy:dy + H, dx:dx + W, tap]
+    ref = torch.nn.functional.conv2d(x, w, padding=1)[0, 0]
+    assert (out - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-6
+    # columns of taps 9..11 (n-tile 2, n >= 2) are zero
+    assert float(Bm[2, :, :, 2:].abs().max()) == 0.0
