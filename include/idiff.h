@@ -187,8 +187,9 @@ int idiff_stem_conv7_tc(const float* x, const float* mu, const void* w_packed, v
 int idiff_stem_packed_bytes(void);
 
 /* Head: 3x3 conv C = 64 -> 1 channel, fp32 out [B,1,H,W], on warp-level tensor-core MMAs (mma.sync m16n8k16).
- * w: the B fragments packed by instancediff_b200/packing.py::pack_head_weight (bf16 hi + lo parts of the fp32
- * weights in MMA columns 0 / 1, 9216 bytes). */
+ * w: the B fragments packed by instancediff_b200/packing.py::pack_head_weight -- [3 n-tiles][4 k-chunks][32 lanes]
+ * (b0, b1), the 9 taps on the N side as (bf16 hi, bf16 lo) column pairs of the fp32 weights, 3072 bytes, 16-byte
+ * aligned.  The kernel forms 9 dot products per input pixel of a tile's patch and gathers them per output pixel. */
 int idiff_head_conv3(const void* src, const void* w, float bias, float* out, int B, int H, int W, int C,
                      void* stream);
 
