@@ -107,3 +107,22 @@ def test_cleanup_matches_the_reference_executed_on_the_same_keys(golden_dir):
     for mode, dist in (("single", False), ("dist", True)):
         got = [[k, v] for k, v in C.clean_state_dict_keys(state, dist=dist).items()]
         assert got == g[mode], mode
+
+
+def test_cleanup_properties():
+    """Single-process clean-up is idempotent and leaves no 'module.' behind; the dist flavour is idempotent too and
+    never changes a key that has no wrapper level to fix."""
+    from hypothesis import given, settings, strategies as st
+    part = st.sampled_from(["module", "ema_model", "online_model", "CLIP_ScoreMapModule", "conv1", "weight", "0", "submodule"])
+    keys = st.lists(part, min_size=1, max_size=6).map(".".join)
+
+    @settings(max_examples=300, deadline=None)
+    @given(keys)
+    def check(k):
+        s = C.clean_key(k, dist=False)
+        assert "module." not in s and C.clean_key(s, dist=False) == s
+        d = C.clean_key(k, dist=True)
+        assert C.clean_key(d, dist=True) == d or d.startswith("module.")     # 'module.module.x' loses one level per pass
+        if not any(w in k for w in ("module", "ema_model", "online_model", "CLIP_ScoreMapModule")):
+            assert d == k == s
+    check()

@@ -277,3 +277,19 @@ def test_head_weight_fragments_reproduce_the_convolution():
     assert (out - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-6
     # columns of taps 9..11 (n-tile 2, n >= 2) are zero
     assert float(Bm[2, :, :, 2:].abs().max()) == 0.0
+
+
+def test_shard_bounds_properties():
+    """Shards are contiguous, ordered, cover [0, total) exactly once and differ in size by at most one."""
+    from hypothesis import given, settings, strategies as st
+    from instancediff_b200 import shard_bounds
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 5000), st.integers(1, 64))
+    def check(total, world):
+        bounds = [shard_bounds(total, world, r) for r in range(world)]
+        assert bounds[0][0] == 0 and bounds[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
+        sizes = [hi - lo for lo, hi in bounds]
+        assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    check()
