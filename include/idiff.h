@@ -7,7 +7,8 @@
  *
  * Conventions: plain pointers and sizes only (no torch types); every pointer is a DEVICE
  * pointer unless the name ends in _host; `stream` is a cudaStream_t passed as void*; calls are
- * stream-ordered and never synchronise; return 0 on success, a negative idiff_status otherwise
+ * stream-ordered and never synchronise -- except idiff_watchdog_status and idiff_debug_read_prof, which say
+ * so (the Python loops call the former ONCE after the last step); return 0 on success, a negative idiff_status otherwise
  * (idiff_last_error() gives the text); nothing throws across the boundary; no CPU fallback.
  * Activations are channels-last (NHWC) bf16; x / mu / eps / z are fp32 [B,1,H,W].
  */
@@ -94,8 +95,8 @@ int idiff_philox_normal(float* out, uint64_t seed, uint64_t elem_offset, uint32_
 int idiff_step_select(const float* table, int* t_counter, float* cur_row, float* cur_time, float sample_scale,
                       void* stream);
 
-/* Bring-up switches used by tests/test_umma_probe.py only (bit 1: swap LBO/SBO of the MN-major V
- * descriptor in self-attention; bit 2: swap LBO/SBO of its K-major descriptors). 0 in production. */
+/* Descriptor bring-up switches (bit 1: swap LBO/SBO of the MN-major V descriptor in self-attention; bit 2: swap
+ * LBO/SBO of its K-major descriptors).  0 in production; no shipped test sets them. */
 int idiff_set_debug_flags(int flags);
 /* Per-role cycle counters of CTA 0 of the last idiff_conv_gemm launched with params.reserved0 = 1
  * (16 x uint64, layout documented in csrc/conv_gemm.cu); synchronises the device. Profiling aid. */

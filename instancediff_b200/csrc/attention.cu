@@ -401,11 +401,12 @@ using namespace idiff;
 int idiff_self_attention(const void* qkv, void* out, int B, int L, int heads, float scale, void* stream) {
   IDIFF_REQUIRE(qkv && out && B > 0 && L > 0 && heads > 0, "self_attention: bad arguments");
   IDIFF_REQUIRE(aligned16(qkv) && aligned16(out), "self_attention: 16 B alignment");
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(self_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+  static DeviceOnce once;
+  {
+    cudaError_t e = per_device_setup(once, nullptr, [] {
+      return cudaFuncSetAttribute(self_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    });
     if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "self_attention attr: %s", cudaGetErrorString(e));
-    attr = true;
   }
   dim3 grid((unsigned)((L + 127) / 128), (unsigned)heads, (unsigned)B);
   self_attention_kernel<<<grid, 128, AT_SMEM, as_stream(stream)>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, L,
@@ -431,11 +432,12 @@ int idiff_linattn_context(const void* qkv, const float* w_out, void* weff_packed
   const int nchunk = (HW + la_chunk(HW) - 1) / la_chunk(HW);
   float* part = scratch;
   float* pmax = scratch + (size_t)B * nchunk * LA_PART;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(linattn_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LA_SMEM);
+  static DeviceOnce once;
+  {
+    cudaError_t e = per_device_setup(once, nullptr, [] {
+      return cudaFuncSetAttribute(linattn_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LA_SMEM);
+    });
     if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "linattn attr: %s", cudaGetErrorString(e));
-    attr = true;
   }
   dim3 grid((unsigned)nchunk, (unsigned)B);
   linattn_kmax_kernel<<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)qkv, pmax, HW);

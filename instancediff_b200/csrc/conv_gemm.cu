@@ -213,12 +213,11 @@ int idiff_conv_gemm(const idiff_gemm_params* pp, void* stream) {
     if (!rc && pp->res1) rc = make_map(&a.tm_res1, pp->res1, pp->N, pp->N, pp->B, pp->H, pp->W);
     if (rc) return rc;
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) { num_sms = 0; return fail(IDIFF_ERR_CUDA, "conv_gemm setup: %s", cudaGetErrorString(e)); }
+  static DeviceOnce once;
+  int num_sms = 0;
+  {
+    cudaError_t e = per_device_setup(once, &num_sms, [] { return cudaSuccess; });
+    if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "conv_gemm setup: %s", cudaGetErrorString(e));
   }
   // persistent: one CTA per SM (TMEM: 2*NT columns each), items strided by the grid size
   const int grid = a.total_items < num_sms ? a.total_items : num_sms;

@@ -898,13 +898,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
 template <int NT, int KS, int EPI, int AMODE>
 inline cudaError_t launch_one(const KArgs& a, int grid, int smem, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<NT, KS, EPI, AMODE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
+  static DeviceOnce once;                     // one flag set per instantiation, one bit per device
+  cudaError_t e = per_device_setup(once, nullptr, [] {
+    return cudaFuncSetAttribute(conv_gemm_kernel<NT, KS, EPI, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kSmemLimit);
+  });
+  if (e != cudaSuccess) return e;
   conv_gemm_kernel<NT, KS, EPI, AMODE><<<grid, kThreads, smem, st>>>(a);
   return cudaSuccess;
 }

@@ -228,14 +228,13 @@ int idiff_head_conv3(const void* src, const void* w, float bias, float* out, int
                      void* stream) {
   IDIFF_REQUIRE(src && w && out && B > 0 && H > 0 && W > 0 && aligned16(w) && aligned16(src), "head_conv3: bad arguments");
   IDIFF_REQUIRE(C == 64, "head_conv3: C must be 64 (got %d)", C);
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(head_conv3_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HM_SMEM);
-    if (e != cudaSuccess) { num_sms = 0; return fail(IDIFF_ERR_CUDA, "head_conv3 setup: %s", cudaGetErrorString(e)); }
+  static DeviceOnce once;
+  int num_sms = 0;
+  {
+    cudaError_t e = per_device_setup(once, &num_sms, [] {
+      return cudaFuncSetAttribute(head_conv3_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HM_SMEM);
+    });
+    if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "head_conv3 setup: %s", cudaGetErrorString(e));
   }
   const int tiles_x = (W + HT - 1) / HT, tiles_y = (H + HT - 1) / HT, total = tiles_x * tiles_y * B;
   const int grid = total < 2 * num_sms ? total : 2 * num_sms;       // 2 resident CTAs per SM

@@ -493,13 +493,15 @@ template <int C>
 static int launch_fused(const void* x, const float* stats, const void* wq, const void* wk, const float* wv,
                         const float* w_out, const float* bias, const float* gain, void* weff, void* out, float* scratch,
                         int B, int HW, float qscale, float eps, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(la_ctx_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtxSmem<C>::TOTAL);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(la_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, OutSmem<C>::TOTAL);
+  static DeviceOnce once;
+  {
+    cudaError_t e = per_device_setup(once, nullptr, [] {
+      cudaError_t e2 = cudaFuncSetAttribute(la_ctx_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtxSmem<C>::TOTAL);
+      if (e2 == cudaSuccess)
+        e2 = cudaFuncSetAttribute(la_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, OutSmem<C>::TOTAL);
+      return e2;
+    });
     if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "linattn_fused attr: %s", cudaGetErrorString(e));
-    attr = true;
   }
   const int nchunk = (HW + lf_chunk(HW) - 1) / lf_chunk(HW);
   float* part = scratch;

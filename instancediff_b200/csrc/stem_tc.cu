@@ -178,14 +178,13 @@ int idiff_stem_conv7_tc(const float* x, const float* mu, const void* w_packed, v
                         void* stream) {
   IDIFF_REQUIRE(x && mu && w_packed && out && B > 0 && H > 0 && W > 0, "stem_conv7_tc: bad arguments");
   IDIFF_REQUIRE(aligned16(w_packed) && aligned16(out), "stem_conv7_tc: 16 B alignment");
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STM_SMEM);
-    if (e != cudaSuccess) { num_sms = 0; return fail(IDIFF_ERR_CUDA, "stem_conv7_tc setup: %s", cudaGetErrorString(e)); }
+  static DeviceOnce once;
+  int num_sms = 0;
+  {
+    cudaError_t e = per_device_setup(once, &num_sms, [] {
+      return cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STM_SMEM);
+    });
+    if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "stem_conv7_tc setup: %s", cudaGetErrorString(e));
   }
   const int tiles_x = (W + STM_TW - 1) / STM_TW, tiles_y = (H + STM_TH - 1) / STM_TH;
   const int total = tiles_x * tiles_y * B;

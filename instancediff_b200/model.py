@@ -29,6 +29,12 @@ class RestorationModel:
                  use_image_context: bool = True, with_drift_net: bool = False, device="cuda", seed: int = 1):
         self.device = torch.device(device)
         self.dist = dist
+        if not use_image_context:
+            # the network's cross-attention layers are built with context_dim = 512 (config.yml:113,132); a forward
+            # without the embedding has no defined meaning in the App. A architecture, so it is refused up front
+            # instead of failing inside test()
+            raise ValueError("RestorationModel: use_image_context=False is not supported -- the B200 network "
+                             "conditions every SpatialTransformer on the image embedding (config.yml:132)")
         self.use_image_context = use_image_context                       # models/drift_noise_model.py:186-189
         self.noise_net = ConditionalUNet(device=self.device, seed=seed, **_net_kwargs(nnet_settings))
         # the reverse-SDE path only consumes the noise net; the drift net is built on request so that both

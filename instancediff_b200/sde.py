@@ -220,6 +220,25 @@ class IRSDE(SDE):
         mu = torch.full_like(x, float(mu))
         return mu, mu.data_ptr()
 
+    def _row_index(self, t) -> int:
+        """Schedule row of step ``t`` with the reference's own indexing rules (``self.thetas[t]``, :179): Python
+        negative indices wrap, anything outside the [sample_T + 1]-row tables raises IndexError -- the row becomes a
+        raw device pointer below, so it is checked here."""
+        n = self._host[0].numel()
+        t = int(t)
+        if not -n <= t < n:
+            raise IndexError(f"index {t} is out of bounds for the schedule tables of size {n}")
+        return t + n if t < 0 else t
+
+    def _check_T(self, T) -> int:
+        """A loop ``for t in reversed(range(1, T + 1))`` indexes rows 1..T (:248): T beyond the tables is the
+        reference's IndexError, not an out-of-bounds device read."""
+        T = int(T)
+        n = self._host[0].numel()
+        if T >= n:
+            raise IndexError(f"index {T} is out of bounds for the schedule tables of size {n}")
+        return T
+
     def _fused_step(self, x, e, t, *, is_score, with_noise, out=None, ode=False):
         """x - drift - dispersion in one pass (replaces :45-46 + :178-179 + :184-185 + :187-188); ``ode`` selects the
         probability-flow drift (:48-49 + :181-182, no dispersion)."""
@@ -230,7 +249,7 @@ class IRSDE(SDE):
         out = torch.empty_like(x) if out is None else out
         mu_keep, mu_ptr = self._mu_ptr(x)
         table = self._coef_table(x.device)
-        coef_ptr = table.data_ptr() + 32 * int(t)
+        coef_ptr = table.data_ptr() + 32 * self._row_index(t)
         z_ptr, philox, z = None, 0, None
         if with_noise:
             if self.noise_source == "philox":
@@ -321,7 +340,7 @@ class IRSDE(SDE):
 
     def reverse_sde(self, xt, T=-1, save_states=False, save_dir="sde_state", **kwargs):
         """The hot loop (:244-261): T sequential (model forward, fused update) pairs, no host sync inside."""
-        T = self.sample_T if T < 0 else T
+        T = self._check_T(self.sample_T if T < 0 else T)
         xt = _require_cuda_f32("xt", xt)
         if T == 0 or xt.numel() == 0:                  # empty loop / empty batch: the reference returns the clone (:247)
             return xt.clone()
@@ -351,7 +370,9 @@ class IRSDE(SDE):
 
     # ---- CUDA-graph replay of one whole step ---------------------------------------------------
     def _graph_eligible(self, xt, save_states, kwargs):
-        return (self.use_cuda_graph and not save_states and self.noise_source == "philox"
+        # noise_source None = torch.randn_like from torch's global CUDA generator (:185): that generator is
+        # capture-aware (its Philox offset is a graph input), so the reference's default noise lives inside the graph
+        return (self.use_cuda_graph and not save_states and (self.noise_source is None or self.noise_source == "philox")
                 and hasattr(self.model, "forward_into") and set(kwargs) == {"image_context"}
                 and torch.is_tensor(self.mu))
 
@@ -361,7 +382,8 @@ class IRSDE(SDE):
         # the Philox stream {seed, offset} lives in device memory, so the captured graph does not depend on it:
         # a data-set loop (one reverse process per item, each with its own offset) replays ONE graph
         off4 = int(self.philox_offset) % 4 == 0
-        key = (tuple(xt.shape), id(self.model), getattr(self.model, "_version", 0), str(dev), off4, ode)
+        torch_noise = (not ode) and self.noise_source is None
+        key = (tuple(xt.shape), id(self.model), getattr(self.model, "_version", 0), str(dev), off4, ode, torch_noise)
         st = self._graph_cache.pop(key, None)
         L = _lib.lib()
         if st is None:
@@ -370,6 +392,7 @@ class IRSDE(SDE):
                       row=torch.zeros(8, dtype=torch.float32, device=dev),
                       time=torch.zeros(1, dtype=torch.float32, device=dev),
                       rng=torch.zeros(2, dtype=torch.int64, device=dev), graph=None,
+                      z=torch.empty_like(xt) if torch_noise else None,
                       model=self.model)                 # keeps id(model) in the key unique while the entry lives
             while len(self._graph_cache) >= self.graph_cache_size:      # oldest entry first (dicts keep order)
                 self._graph_cache.pop(next(iter(self._graph_cache)))
@@ -390,6 +413,10 @@ class IRSDE(SDE):
             if ode:                                     # :48-49 -- no dispersion, half the sigma^2 * score term
                 check(L.idiff_sde_step(st["x"].data_ptr(), st["x"].data_ptr(), eps.data_ptr(), st["mu"].data_ptr(), None,
                                        st["row"].data_ptr(), 2, 0, 0, 0, st["x"].numel(), s), "sde_step")
+            elif torch_noise:                           # z = randn_like(x) (:185), drawn by torch inside the graph
+                st["z"].normal_()
+                check(L.idiff_sde_step(st["x"].data_ptr(), st["x"].data_ptr(), eps.data_ptr(), st["mu"].data_ptr(),
+                                       st["z"].data_ptr(), st["row"].data_ptr(), 0, 0, 0, 0, st["x"].numel(), s), "sde_step")
             else:
                 check(L.idiff_sde_step_rng(st["x"].data_ptr(), st["x"].data_ptr(), eps.data_ptr(), st["mu"].data_ptr(),
                                            st["row"].data_ptr(), 0, st["rng"].data_ptr(), 1 if off4 else 0,
@@ -415,7 +442,7 @@ class IRSDE(SDE):
     def reverse_ode(self, xt, T=-1, save_states=False, save_dir="ode_state", **kwargs):
         """Probability-flow Euler loop (:263-280): model forward + ONE fused update per step.  The reference does not
         forward model kwargs here (:267); they are accepted so a conditioned network can be sampled this way too."""
-        T = self.sample_T if T < 0 else T
+        T = self._check_T(self.sample_T if T < 0 else T)
         xt = _require_cuda_f32("xt", xt)
         if T == 0 or xt.numel() == 0:
             return xt.clone()

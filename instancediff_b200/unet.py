@@ -143,8 +143,10 @@ class ConditionalUNet:
         self._ctx_key = None
         self._ctx_ref = None
         self._crossvec: Dict[tuple, torch.Tensor] = {}
+        self.pk: Optional[Dict[str, dict]] = None    # packed weights: built lazily, ONCE per weight load
+        self._version = 0
         self._init_params(seed)
-        self._pack()
+        self._invalidate()
 
     # ------------------------------------------------------------------ parameters
     def _init_params(self, seed):
@@ -173,7 +175,7 @@ class ConditionalUNet:
                 if tuple(sd[k].shape) != tuple(self.params[k].shape):
                     raise ValueError(f"{k}: shape {tuple(sd[k].shape)} != {tuple(self.params[k].shape)}")
                 self.params[k] = sd[k].detach().to(self.device, torch.float32).contiguous()
-        self._pack()
+        self._invalidate()
         return self
 
     def eval(self):
@@ -188,26 +190,39 @@ class ConditionalUNet:
         if norm(device) != norm(self.device):
             self.device = torch.device(device)
             self.params = {k: v.to(self.device) for k, v in self.params.items()}
-            self._plans.clear()                      # launch plans, workspaces and context vectors live on the old device
-            self._crossvec.clear()
-            self._ctx_key = self._ctx_ref = None
-            self._pack()
+            self._crossvec.clear()                   # context vectors live on the old device
+            self._ctx_ref = None
+            self._invalidate()
         return self
 
     # ------------------------------------------------------------------ packing
+    def _invalidate(self):
+        """The weights changed: drop the packed arena and every launch plan.  Packing itself is deferred to the first
+        forward, so ``ConditionalUNet(...).load_state_dict(sd)`` packs once, not twice."""
+        self.pk = None
+        self._plans.clear()
+        self._ctx_key = None
+        self._version += 1                          # captured graphs hold pointers into the old packing
+
+    def _ensure_packed(self):
+        if self.pk is None:
+            self._pack()
+
     def _pack(self):
-        P = self.params
+        """Host-side packing: every layout transform runs on CPU copies of the parameters, the results are laid out
+        in ONE byte arena and reach the device in a single copy (no ATen kernel launches on the GPU)."""
+        P = {k: v.detach().to("cpu", torch.float32) for k, v in self.params.items()}
         pk: Dict[str, dict] = {}
 
         def f32(t):
-            return t.detach().to(self.device, torch.float32).contiguous()
+            return t.detach().to(torch.float32).contiguous()
 
         def conv_entry(name, NT=None, w=None, b=None, k=None):
             w = P[name + ".weight"] if w is None else w
             b = P.get(name + ".bias") if b is None else b
             N = w.shape[0]
             NT = min(N, 256) if NT is None else NT
-            pk[name] = dict(w=pack_conv_weight(w, NT).to(self.device), bias=None if b is None else f32(b), N=N, NT=NT,
+            pk[name] = dict(w=pack_conv_weight(w, NT), bias=None if b is None else f32(b), N=N, NT=NT,
                             cin=w.shape[1], k=(w.shape[2] if w.dim() == 4 else 1) if k is None else k)
             return pk[name]
 
@@ -231,8 +246,8 @@ class ConditionalUNet:
                                          bias=f32(P[f + ".to_out.bias"]), g=f32(P[f + ".out_norm.g"].reshape(-1)))
                 if dim in (64, 128):                  # fused three-pass kernel: q / k weights packed separately,
                     wg = wq * g_pre[None, :]          # v folded into the merge step (pre-norm gain in the weights)
-                    pk[f + ".fused"] = dict(wq=pack_conv_weight(wg[0:128], 128).to(self.device),
-                                            wk=pack_conv_weight(wg[128:256], 128).to(self.device),
+                    pk[f + ".fused"] = dict(wq=pack_conv_weight(wg[0:128], 128),
+                                            wk=pack_conv_weight(wg[128:256], 128),
                                             wv=f32(wg[256:384]))
             else:
                 pk[prefix + ".prenorm"] = dict(g=f32(g_pre))
@@ -252,8 +267,8 @@ class ConditionalUNet:
                 conv_entry(f + ".proj_out")
 
         # stem / head / time
-        pk["init_conv"] = dict(w=pack_stem_weight(f32(P["init_conv.weight"]), f32(P["init_conv.bias"])).to(self.device))
-        pk["final_conv"] = dict(w=pack_head_weight(f32(P["final_conv.weight"])).to(self.device),
+        pk["init_conv"] = dict(w=pack_stem_weight(f32(P["init_conv.weight"]), f32(P["init_conv.bias"])))
+        pk["final_conv"] = dict(w=pack_head_weight(f32(P["final_conv.weight"])),
                                 bias=float(P["final_conv.bias"].reshape(-1)[0].item()))
         self._res_names: List[str] = []
         n = len(self.io)
@@ -293,10 +308,22 @@ class ConditionalUNet:
         pk["time"] = dict(w1t=f32(P["time_lin1.weight"].t()), b1=f32(P["time_lin1.bias"]),
                           w2t=f32(P["time_lin2.weight"].t()), b2=f32(P["time_lin2.bias"]),
                           wss=f32(torch.cat(ws, 0)), bss=f32(torch.cat(bs, 0)))
+        # one arena, one host-to-device copy: 256 B aligned slices viewed with each tensor's own dtype
+        slots, off = [], 0
+        for entry in pk.values():
+            for key, val in entry.items():
+                if torch.is_tensor(val):
+                    val = val.contiguous()
+                    nb = val.numel() * val.element_size()
+                    slots.append((entry, key, val, off, nb))
+                    off += (nb + 255) // 256 * 256
+        host = torch.empty(max(off, 256), dtype=torch.uint8)
+        for _, _, val, o, nb in slots:
+            host[o:o + nb] = val.reshape(-1).view(torch.uint8)
+        self._arena = host.to(self.device)
+        for entry, key, val, o, nb in slots:
+            entry[key] = self._arena[o:o + nb].view(val.dtype).reshape(val.shape)
         self.pk = pk
-        self._plans.clear()
-        self._ctx_key = None
-        self._version = getattr(self, "_version", 0) + 1     # captured graphs hold pointers into the old packing
 
     # ------------------------------------------------------------------ conditioning
     def spatial_layers(self):
@@ -337,6 +364,7 @@ class ConditionalUNet:
 
     # ------------------------------------------------------------------ forward
     def _plan(self, B, H, W, shared_time) -> "_Plan":
+        self._ensure_packed()
         key = (B, H, W, shared_time)
         if key not in self._plans:
             self._plans[key] = _Plan(self, B, H, W, shared_time)
@@ -375,6 +403,8 @@ class ConditionalUNet:
         return plan.eps
 
     def forward(self, xt, cond, time, *unused, image_context=None, **unused_kw):
+        """``image_context`` is keyword-only like in the reference's call (models/drift_noise_model.py:253) and
+        REQUIRED: the network has no unconditioned mode (raises IdiffError when it is missing)."""
         H, W = xt.shape[-2:]
         if xt.shape[0] == 0:                           # empty batch: nothing to launch
             return torch.empty_like(xt)
