@@ -171,6 +171,21 @@ int idiff_conv_gemm_smem_bytes(const idiff_gemm_params* p);
  * argument of idiff_gn_finalize): 4 per 16x8-pixel tile, one per epilogue warp. */
 int idiff_conv_gemm_gn_rows(int H, int W);
 
+/* 3x3 / stride 1 / 64 -> 64 convolution on FULL-WIDTH MMAs ("row-pair" formulation, csrc/conv3_rowpair.cu): one work
+ * item = 2 output rows x 128 pixels; A = one input row of the strip (shifted descriptor per filter column), the N
+ * side stacks the two output rows ([W(dy); W(dy-1)] windows of one weight buffer): 4 x 64 tensor cycles per filter
+ * column and K16 step for 256 output pixels instead of 6 x 64 in idiff_conv_gemm, whose M128 x N64 MMAs are bound by
+ * the shared-memory read of A.  Input rows live in a ring of row-pair stages (each row is read once per strip).
+ * Same params struct; accepted subset = idiff_conv3_rowpair_supported(p): ksize 3, stride 1, cin0 = N = NT = 64,
+ * cin1 = 0, no upsampling, plain epilogue, no residuals / row statistics, even H, A transform none or affine+SiLU,
+ * optional GroupNorm partial sums.  p->w must be packed by packing.py::pack_conv3_rowpair (73728 bytes).
+ * a_silu bit 1 (value 3) evaluates the loader's affine + SiLU in packed bf16x2 arithmetic (fma.rn.bf16x2 /
+ * tanh.approx.bf16x2: 12 instead of 36 instructions per 8 channels; the transformed operand is bf16 either way).
+ * gn_partial rows per image: idiff_conv3_rowpair_gn_rows(H, W) = 4 per output row and 128-pixel strip. */
+int idiff_conv3_rowpair(const idiff_gemm_params* p, void* stream);
+int idiff_conv3_rowpair_supported(const idiff_gemm_params* p);
+int idiff_conv3_rowpair_gn_rows(int H, int W);
+
 /* Plain CUDA-core convolution over the same params subset (ksize, stride, cin0/cin1, up0, a_*,
  * bias, PLAIN epilogue, fp32 weights [N][k][k][cin]).  Used for validation of the tensor-core path. */
 int idiff_conv_ref(const idiff_gemm_params* p, const float* w_f32, float* out_f32, void* stream);

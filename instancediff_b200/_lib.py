@@ -57,6 +57,9 @@ SIGNATURES = {
     "idiff_sizeof_gemm_params": (C.c_int, []),
     "idiff_conv_gemm_smem_bytes": (C.c_int, [C.POINTER(GemmParams)]),
     "idiff_conv_gemm_gn_rows": (C.c_int, [C.c_int, C.c_int]),
+    "idiff_conv3_rowpair": (C.c_int, [C.POINTER(GemmParams), c_ptr]),
+    "idiff_conv3_rowpair_supported": (C.c_int, [C.POINTER(GemmParams)]),
+    "idiff_conv3_rowpair_gn_rows": (C.c_int, [C.c_int, C.c_int]),
     "idiff_conv_ref": (C.c_int, [C.POINTER(GemmParams), c_ptr, c_ptr, c_ptr]),
     "idiff_stem_conv7": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr]),
     "idiff_stem_conv7_tc": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr]),

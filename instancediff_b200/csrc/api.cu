@@ -30,9 +30,9 @@ int idiff_watchdog_status(int clear) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return idiff::fail(IDIFF_ERR_CUDA, "watchdog sync: %s", cudaGetErrorString(e));
   const int a = idiff::watchdog_conv(clear), b = idiff::watchdog_attn(clear), c = idiff::watchdog_stem(clear),
-            d = idiff::watchdog_lattn(clear);
-  if (a < 0 || b < 0 || c < 0 || d < 0) return idiff::fail(IDIFF_ERR_CUDA, "watchdog read failed");
-  const int v = a != 0 ? a : (b != 0 ? b : (c != 0 ? c : d));
+            d = idiff::watchdog_lattn(clear), r = idiff::watchdog_rowpair(clear);
+  if (a < 0 || b < 0 || c < 0 || d < 0 || r < 0) return idiff::fail(IDIFF_ERR_CUDA, "watchdog read failed");
+  const int v = a != 0 ? a : (b != 0 ? b : (c != 0 ? c : (d != 0 ? d : r)));
   if (v != 0) idiff::fail(IDIFF_ERR_WATCHDOG, "device pipeline wait timed out at site %d", v);
   return v;
 }

@@ -139,12 +139,17 @@ static EncodeTiledFn encode_fn() {
 }
 // bf16 [B][H][W][ld] tensor of which `cols` channels are addressed; box = 64 channels x 8 x 4 pixels (one epilogue
 // warp's share of a tile), 128B swizzle.  Out-of-range box parts are clipped (stores) / zero-filled (loads).
+int make_map_box(CUtensorMap* tm, const void* base, int cols, int ld, int B, int H, int W, int box_w, int box_h);
 static int make_map(CUtensorMap* tm, const void* base, int cols, int ld, int B, int H, int W) {
+  return make_map_box(tm, base, cols, ld, B, H, W, TILE_W, 4);
+}
+// general form: box = 64 channels x box_w x box_h pixels (conv3_rowpair.cu stores 32 x 1 pixel rows)
+int make_map_box(CUtensorMap* tm, const void* base, int cols, int ld, int B, int H, int W, int box_w, int box_h) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(IDIFF_ERR_CUDA, "conv_gemm: cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-  const cuuint32_t box[4] = {64, (cuuint32_t)TILE_W, 4, 1};
+  const cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -154,6 +159,10 @@ static int make_map(CUtensorMap* tm, const void* base, int cols, int ld, int B, 
 }
 
 static unsigned long long* g_prof_dev = nullptr;
+unsigned long long* prof_buffer() {                 // shared with conv3_rowpair.cu (profiling builds)
+  if (!g_prof_dev && cudaMalloc(&g_prof_dev, 16 * sizeof(unsigned long long)) != cudaSuccess) g_prof_dev = nullptr;
+  return g_prof_dev;
+}
 
 }  // namespace idiff
 

@@ -15,6 +15,7 @@ int watchdog_conv(int clear);   // conv_gemm.cu
 int watchdog_attn(int clear);   // attention.cu
 int watchdog_stem(int clear);   // stem_tc.cu
 int watchdog_lattn(int clear);  // linattn_fused.cu
+int watchdog_rowpair(int clear);  // conv3_rowpair.cu
 // One-time PER-DEVICE launch setup: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to the
 // current device, so a process that drives several GPUs (ConditionalUNet.to(other), two nets on two devices) must
 // repeat it on each.  Thread-safe: a racing second thread at worst repeats the idempotent setup.

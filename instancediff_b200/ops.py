@@ -41,6 +41,12 @@ def conv_gemm(p: GemmParams, stream: Optional[int] = None) -> None:
     check(_lib.lib().idiff_conv_gemm(C.byref(p), s), "conv_gemm")
 
 
+def conv3_rowpair(p: GemmParams, stream: Optional[int] = None) -> None:
+    """Row-pair full-width-MMA kernel for 3x3 64 -> 64 layers (``p.w`` packed by ``pack_conv3_rowpair``)."""
+    s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+    check(_lib.lib().idiff_conv3_rowpair(C.byref(p), s), "conv3_rowpair")
+
+
 def conv_ref(p: GemmParams, w_f32: torch.Tensor, out_f32: torch.Tensor) -> None:
     check(_lib.lib().idiff_conv_ref(C.byref(p), w_f32.data_ptr(), out_f32.data_ptr(), _s(out_f32)), "conv_ref")
 

@@ -28,6 +28,20 @@ def pack_conv_weight(w: torch.Tensor, NT: int) -> torch.Tensor:
     return t.to(torch.bfloat16).reshape(-1)
 
 
+def pack_conv3_rowpair(w: torch.Tensor) -> torch.Tensor:
+    """w: [64, 64, 3, 3] fp32 -> the resident B operand of ``idiff_conv3_rowpair``:
+
+        packed[dx][c8][blk][n][e]      bf16,   blk = 0, 1, 2  <->  filter row dy = 2, 1, 0
+
+    Per filter column dx and 8-channel plane c8 the three filter rows are stacked along N (64 output channels each),
+    so the N = 128 windows [W(dy=2); W(dy=1)] and [W(dy=1); W(dy=0)] and the N = 64 windows W(2), W(0) are the same
+    buffer viewed from a shifted start address (LBO = 3072 B between planes, SBO = 128 B)."""
+    assert tuple(w.shape) == (64, 64, 3, 3), w.shape
+    t = w.permute(3, 1, 2, 0).reshape(3, 8, 8, 3, 64)      # dx, c8, e, dy, n
+    t = t.flip(3).permute(0, 1, 3, 4, 2).contiguous()      # dx, c8, blk (dy = 2,1,0), n, e
+    return t.to(torch.bfloat16).reshape(-1)
+
+
 def unpack_conv_weight(p: torch.Tensor, N: int, Cin: int, k: int, NT: int) -> torch.Tensor:
     """Inverse of pack_conv_weight (tests)."""
     t = p.reshape(N // NT, Cin // 64, k * k, 8, NT, 8).permute(0, 4, 2, 1, 3, 5)

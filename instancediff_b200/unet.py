@@ -15,13 +15,15 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
 
 from . import _lib
 from ._lib import EPI_GEGLU, EPI_LN_OUT, EPI_PLAIN, EPI_QSOFTMAX, GemmParams, check
-from .packing import fold_layernorm, interleave_geglu, pack_conv_weight, pack_head_weight, pack_stem_weight
+from .packing import (fold_layernorm, interleave_geglu, pack_conv3_rowpair, pack_conv_weight, pack_head_weight,
+                      pack_stem_weight)
 
 GN_GROUPS = 8
 TILE_H, TILE_W = 16, 8
@@ -143,6 +145,10 @@ class ConditionalUNet:
         self._ctx_key = None
         self._ctx_ref = None
         self._crossvec: Dict[tuple, torch.Tensor] = {}
+        # 3x3 64 -> 64 layers on the full-width-MMA row-pair kernel (csrc/conv3_rowpair.cu); IDIFF_NO_ROWPAIR=1 keeps
+        # them on the generic engine (A/B measurements)
+        self.use_rowpair = os.environ.get("IDIFF_NO_ROWPAIR", "0") != "1"
+        self.rowpair_packed_silu = os.environ.get("IDIFF_ROWPAIR_F32_SILU", "0") != "1"
         self.pk: Optional[Dict[str, dict]] = None    # packed weights: built lazily, ONCE per weight load
         self._version = 0
         self._init_params(seed)
@@ -224,6 +230,8 @@ class ConditionalUNet:
             NT = min(N, 256) if NT is None else NT
             pk[name] = dict(w=pack_conv_weight(w, NT), bias=None if b is None else f32(b), N=N, NT=NT,
                             cin=w.shape[1], k=(w.shape[2] if w.dim() == 4 else 1) if k is None else k)
+            if tuple(w.shape) == (64, 64, 3, 3):          # second packing for idiff_conv3_rowpair
+                pk[name]["w_rp"] = pack_conv3_rowpair(w)
             return pk[name]
 
         def resblock(prefix):
@@ -487,7 +495,15 @@ class _Plan:
             self.ctx_slots[bias_img_slot] = p
         self.keep.append(p)
         L, ref = self.L, C.byref(p)
-        self.ops.append(lambda s: check(L.idiff_conv_gemm(ref, s), "conv_gemm"))
+        rp = w_override is None and self.rowpair_ok(entry, src0, src1, out, k, stride, up) and bool(
+            L.idiff_conv3_rowpair_supported(ref))
+        if rp:
+            p.w = _ptr(entry["w_rp"])
+            if a_silu and self.net.rowpair_packed_silu:
+                p.a_silu = 3                      # bit 1: affine + SiLU of the loader in packed bf16x2 arithmetic
+            self.ops.append(lambda s: check(L.idiff_conv3_rowpair(ref, s), "conv3_rowpair"))
+        else:
+            self.ops.append(lambda s: check(L.idiff_conv_gemm(ref, s), "conv_gemm"))
         flops = 2.0 * self.B * out.H * out.W * p.N * (p.cin0 + p.cin1) * k * k
         # algorithmic HBM bytes: every source pixel once, every output element once, residuals once (bf16)
         px_out = self.B * out.H * out.W
@@ -496,8 +512,23 @@ class _Plan:
         nbytes = 2.0 * (px_in * (p.cin0 + p.cin1) + px_out * out_cols
                         + px_out * p.N * ((res0 is not None) + (res1 is not None)))
         self.op_bytes[len(self.ops) - 1] = nbytes
-        self.op_info.append(("conv_gemm", flops, f"k{k}s{stride}u{up} {p.cin0 + p.cin1}->{p.N} @{out.H}x{out.W}"))
+        self.op_info.append(("conv_gemm", flops, f"k{k}s{stride}u{up} {p.cin0 + p.cin1}->{p.N} @{out.H}x{out.W}"
+                             + (" rowpair" if rp else "")))
         self.n_launch += 1
+
+    def rowpair_ok(self, entry, src0, src1, out, k=3, stride=1, up=0) -> bool:
+        """Layer shape the row-pair kernel is built for AND worth it: strips are 128 pixels wide, so narrow or ragged
+        rows waste MMA rows (efficiency = W / (strips * 128))."""
+        if not self.net.use_rowpair or "w_rp" not in entry or src1 is not None or k != 3 or stride != 1 or up:
+            return False
+        W = out.W
+        return out.H % 2 == 0 and W / (-(-W // 128) * 128) >= 0.74
+
+    def gn_rows(self, entry, src0, src1, out):
+        """rows of GroupNorm partial sums per image the kernel chosen for this layer writes"""
+        if self.rowpair_ok(entry, src0, src1, out):
+            return self.L.idiff_conv3_rowpair_gn_rows(out.H, out.W)
+        return self.L.idiff_conv_gemm_gn_rows(out.H, out.W)
 
     def bind_context(self, crossvec):
         for name, p in self.ctx_slots.items():
@@ -530,17 +561,18 @@ class _Plan:
     def resblock(self, prefix, src0: _Act, src1: Optional[_Act], cout, want_stats=False) -> _Act:
         pk, B, H, W = self.net.pk, self.B, src0.H, src0.W
         cin = src0.C + (src1.C if src1 is not None else 0)
-        ntile = self.tiles(H, W)
         count = H * W * (cout // GN_GROUPS)
-        part1 = self.tmp("gnp1", (B, ntile, GN_GROUPS, 2), torch.float32)
-        part2 = self.tmp("gnp2", (B, ntile, GN_GROUPS, 2), torch.float32)
         y1 = self.act(H, W, cout, tmp_name="y1")
         y2 = self.act(H, W, cout, tmp_name="y2")
+        nt1 = self.gn_rows(pk[prefix + ".conv1"], src0, src1, y1)
+        nt2 = self.gn_rows(pk[prefix + ".conv2"], y1, None, y2)
+        part1 = self.tmp("gnp1", (B, nt1, GN_GROUPS, 2), torch.float32)
+        part2 = self.tmp("gnp2", (B, nt2, GN_GROUPS, 2), torch.float32)
         self.gemm(src0, src1, pk[prefix + ".conv1"], y1, k=3, gn_partial=part1)
-        sc1, sh1 = self.gn_finalize(part1, ntile, pk[prefix + ".norm1"], cout, GN_GROUPS, count, 1e-5,
+        sc1, sh1 = self.gn_finalize(part1, nt1, pk[prefix + ".norm1"], cout, GN_GROUPS, count, 1e-5,
                                     t_off=self.net._ss_off[prefix], tag="gn1")
         self.gemm(y1, None, pk[prefix + ".conv2"], y2, k=3, a_scale=sc1, a_shift=sh1, a_silu=1, gn_partial=part2)
-        sc2, sh2 = self.gn_finalize(part2, ntile, pk[prefix + ".norm2"], cout, GN_GROUPS, count, 1e-5, tag="gn2")
+        sc2, sh2 = self.gn_finalize(part2, nt2, pk[prefix + ".norm2"], cout, GN_GROUPS, count, 1e-5, tag="gn2")
         out = self.act(H, W, cout, stats=want_stats)
         if cin == cout:
             L = self.L

@@ -91,6 +91,93 @@ def test_conv_matches_fp32_reference(case):
     assert rel_err(out, ref) <= TOL, describe(out, ref, str(case))
 
 
+def _run_rowpair(B, H, W, affine, seed=0, gn=False, packed=False):
+    """idiff_conv3_rowpair (full-width MMA formulation of the 3x3 64 -> 64 layers) on the same contract."""
+    from instancediff_b200 import _lib, ops
+    from instancediff_b200.packing import pack_conv3_rowpair
+    g = torch.Generator().manual_seed(seed)
+    src0 = rand_act(B, H, W, 64, g)
+    w = (torch.rand(64, 64, 3, 3, generator=g) * 2 - 1).cuda() / math.sqrt(64 * 9)
+    bias = (torch.rand(64, generator=g) * 2 - 1).cuda() * 0.1
+    sc = sh = None
+    if affine:
+        sc = (torch.rand(B, 64, generator=g) + 0.5).cuda()
+        sh = (torch.rand(B, 64, generator=g) - 0.5).cuda()
+    out = torch.full((B, H, W, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    rows = _lib.lib().idiff_conv3_rowpair_gn_rows(H, W)
+    part = torch.full((B, rows, 8, 2), float("nan"), device="cuda") if gn else None
+    p = ops.make_gemm_params(B=B, H=H, W=W, ksize=3, stride=1, cin0=64, N=64, NT=64, a_silu=int(affine) * (3 if packed else 1),
+                             epi=0, out_ld=64, src0=src0, a_scale=sc, a_shift=sh, w=pack_conv3_rowpair(w.cpu()).cuda(), bias=bias,
+                             out=out, gn_groups=8 if gn else 0, gn_partial=part)
+    assert _lib.lib().idiff_conv3_rowpair_supported(p)
+    ops.conv3_rowpair(p)
+    torch.cuda.synchronize()
+    ref = conv_reference(src0, None, w, bias, 3, 1, 0, sc, sh, affine)
+    return out, ref, part
+
+
+ROWPAIR_CASES = [
+    # B, H, W, affine+SiLU
+    (1, 2, 128, False),          # one item: both row pairs are the image border
+    (2, 32, 128, False),
+    (1, 16, 256, True),          # two strips per row
+    (1, 8, 40, True),            # image narrower than a strip (clipped TMA store, zero-filled loads)
+    (1, 24, 200, True),          # ragged second strip (72 of 128 pixels)
+    (3, 64, 256, False),         # 192 items: every CTA of the grid has work
+    (4, 128, 256, True),         # 512 items on 148 CTAs: item ranges start and end in the middle of a strip
+    (2, 30, 144, False),         # H/2 odd, ragged strip
+]
+
+
+@pytest.mark.parametrize("case", ROWPAIR_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_rowpair_conv_matches_fp32_reference(case):
+    B, H, W, aff = case
+    out, ref, _ = _run_rowpair(B, H, W, aff, seed=H + W)
+    assert not torch.isnan(out.float()).any(), "unwritten output pixels"
+    assert rel_err(out, ref) <= TOL, describe(out, ref, "rowpair " + str(case))
+
+
+def test_rowpair_packed_bf16x2_transform_stays_inside_the_tolerance():
+    """a_silu = 3: affine + SiLU of the loader in packed bf16x2 arithmetic (scale / shift rounded to bf16, tanh in bf16).
+    The A operand is bf16 on both paths; the packed evaluation adds two bf16 roundings before it."""
+    for case in [(1, 16, 256), (2, 64, 128), (1, 24, 200)]:
+        out, ref, _ = _run_rowpair(*case, True, seed=3, packed=True)
+        exact, _, _ = _run_rowpair(*case, True, seed=3, packed=False)
+        assert rel_err(out, ref) <= TOL, describe(out, ref, "rowpair packed " + str(case))
+        assert rel_err(out, ref) <= 3 * rel_err(exact, ref) + 2e-3
+
+
+def test_rowpair_conv_equals_the_generic_engine_and_writes_groupnorm_partials():
+    """Same layer through both kernels: identical bf16 inputs, fp32 accumulation in a different order -> equal up to
+    the bf16 rounding of the output; GroupNorm partial sums (own row layout) finalize to torch's GroupNorm."""
+    from instancediff_b200 import ops
+    B, H, W = 2, 32, 256
+    out, ref, part = _run_rowpair(B, H, W, True, seed=5, gn=True)
+    gen, ref2, _ = _run(B, H, W, 64, 0, 64, 3, affine=True, silu=True, seed=5)
+    assert not torch.isnan(part).any(), "unwritten GroupNorm partial rows"
+    s = part.sum(dim=1)
+    r = ref.reshape(B, H * W, 8, 8)
+    assert torch.allclose(s[..., 0], r.sum(dim=(1, 3)), rtol=1e-3, atol=1e-2), (s[..., 0], r.sum(dim=(1, 3)))
+    assert torch.allclose(s[..., 1], (r * r).sum(dim=(1, 3)), rtol=1e-3, atol=1e-2)
+    gamma, beta = torch.rand(64, device="cuda") + 0.5, torch.rand(64, device="cuda") - 0.5
+    sc, sh = ops.gn_finalize(part, gamma, beta, H * W * 8, 1e-5)
+    y = ref * sc[:, None, None, :] + sh[:, None, None, :]
+    gn = F.group_norm(ref.permute(0, 3, 1, 2), 8, gamma, beta, 1e-5).permute(0, 2, 3, 1)
+    assert rel_err(y, gn) <= 1e-3, describe(y, gn, "gn")
+    assert rel_err(out, ref) <= TOL, describe(out, ref, "rowpair")
+
+
+def test_rowpair_rejects_unsupported_layers():
+    from instancediff_b200 import _lib, ops
+    x = torch.zeros(1, 16, 128, 64, dtype=torch.bfloat16, device="cuda")
+    ok = dict(B=1, H=16, W=128, ksize=3, stride=1, cin0=64, N=64, NT=64, out_ld=64, src0=x, w=x, out=x)
+    for bad in (dict(cin1=64, src1=x), dict(N=128, NT=128, out_ld=128), dict(ksize=1), dict(res0=x), dict(H=15), dict(up0=1)):
+        p = ops.make_gemm_params(**{**ok, **bad})
+        assert not _lib.lib().idiff_conv3_rowpair_supported(p)
+        with pytest.raises(_lib.IdiffError):
+            ops.conv3_rowpair(p)
+
+
 def test_cuda_core_reference_agrees():
     """idiff_conv_ref (plain CUDA-core loop nest) is an independent check of the same params struct."""
     from instancediff_b200 import ops

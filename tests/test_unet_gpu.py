@@ -20,8 +20,8 @@ pytestmark = pytest.mark.gpu
 # well inside the 1e-2 per-step gate that test_sampler_teacher_forced_per_step_and_final_psnr enforces directly.
 EPS_TOL = 2e-2
 # Free-running 100-step loop, CUDA path vs oracle, same pre-drawn noise (measured: see profiles/r02_parity.json)
-FREE_RUN_DRIFT_TOL = 0.10
-FREE_RUN_PSNR_DB = 30.0
+FREE_RUN_DRIFT_TOL = 2e-2      # max |x_out - x_oracle| / max |x_oracle| after 100 free-running steps
+FREE_RUN_PSNR_DB = 45.0        # 20 log10(max |x_oracle| / rms(x_out - x_oracle))
 
 
 def _record(key, values):
@@ -167,7 +167,10 @@ def test_sampler_teacher_forced_per_step_and_final_psnr(nets, shape):
     x_out = sde.reverse_sde(x, T=-1, image_context=ctx)
     d_psnr = abs(_psnr(x_out, gt) - _psnr(x_ref, gt))
     drift = rel_err(x_out, x_ref)
-    psnr_direct = _psnr(x_out, x_ref)                      # pointwise: restored image vs the oracle's restored image
+    # pointwise: restored image vs the oracle's restored image, peak = the oracle image's own amplitude (with random
+    # weights the loop diverges to |x| >> 1, so a data_range = 1 PSNR would measure that amplitude, not the agreement)
+    rms = (x_out - x_ref).double().pow(2).mean().sqrt().item()
+    psnr_direct = 20 * math.log10(x_ref.abs().max().item() / max(rms, 1e-30))
     _record("free_run_" + "x".join(map(str, shape)), dict(teacher_forced_worst=worst, d_psnr_vs_pseudo_gt=d_psnr,
                                                          drift_rel=drift, psnr_vs_oracle_db=psnr_direct))
     assert d_psnr <= 0.05, f"|dPSNR|={d_psnr:.4f} dB (free-run drift {drift:.4g})"
