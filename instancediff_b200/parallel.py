@@ -23,7 +23,8 @@ class _Bucket:
     def __init__(self, params: List[torch.nn.Parameter]):
         self.params = params
         self.numel = sum(p.numel() for p in params)
-        self.flat: Optional[torch.Tensor] = None
+        self.flat: Optional[torch.Tensor] = None          # the gradients of this bucket LIVE here (p.grad are views)
+        self.wire: Optional[torch.Tensor] = None          # communication copy when comm_dtype differs
         self.pending = len(params)
         self.handle = None
 
@@ -31,8 +32,13 @@ class _Bucket:
 class GradientAllReducer:
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_mb: float = 25.0, process_group=None,
                  comm_dtype: Optional[torch.dtype] = None):
-        """``comm_dtype``: dtype of the flat communication buffers (``torch.bfloat16`` halves the bytes on the wire,
-        46 MB instead of 91 MB per network; the division and the write-back stay in the gradient's dtype)."""
+        """``comm_dtype``: dtype of the buffers on the wire (``torch.bfloat16`` halves the bytes, 46 MB instead of 91 MB
+        per network; the gradients themselves stay in the parameter dtype).
+
+        Every bucket owns ONE flat buffer and the ``.grad`` of its parameters are views into it (what DDP calls
+        ``gradient_as_bucket_view``): backward accumulates straight into the communication buffer, the all-reduce runs
+        in place and nothing is copied per parameter -- with 343 parameter tensors the copy-in / copy-out variant spent
+        8 ms per step in ~1000 tiny kernels for a transfer that takes well under a millisecond on NVLink."""
         self.group = process_group
         self.comm_dtype = comm_dtype
         plist = [p for p in params if p.requires_grad]
@@ -53,9 +59,35 @@ class GradientAllReducer:
         self._owner = {id(p): b for b in self.buckets for p in b.params}
         self._hooks = []
 
+    def _materialize(self, b: _Bucket) -> None:
+        """(Re)build the flat buffer and point every ``.grad`` of the bucket into it, keeping existing gradients."""
+        ref = b.params[0]
+        intact = b.flat is not None and b.flat.device == ref.device and b.flat.dtype == ref.dtype
+        if intact:
+            off = 0
+            for p in b.params:
+                n = p.numel()
+                if p.grad is None or p.grad.data_ptr() != b.flat.data_ptr() + off * b.flat.element_size():
+                    intact = False
+                    break
+                off += n
+        if intact:
+            return
+        flat = torch.zeros(b.numel, dtype=ref.dtype, device=ref.device)
+        off = 0
+        for p in b.params:
+            n = p.numel()
+            view = flat[off:off + n].view_as(p)
+            if p.grad is not None:
+                view.copy_(p.grad)
+            p.grad = view
+            off += n
+        b.flat = flat
+
     # ---- automatic mode: fire buckets from inside backward --------------------------------------------------
     def attach(self) -> "GradientAllReducer":
         for b in self.buckets:
+            self._materialize(b)
             for p in b.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
         return self
@@ -64,6 +96,13 @@ class GradientAllReducer:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+
+    def zero_grad(self) -> None:
+        """Start of a step (replaces ``optimizer.zero_grad``): one fill per bucket, the views stay in place."""
+        for b in self.buckets:
+            self._materialize(b)
+            b.flat.zero_()
+            b.pending = len(b.params)
 
     def _on_grad(self, p: torch.nn.Parameter) -> None:
         b = self._owner[id(p)]
@@ -80,35 +119,23 @@ class GradientAllReducer:
         return self
 
     def _launch(self, b: _Bucket) -> None:
-        ref = b.params[0]
-        dtype = self.comm_dtype or ref.dtype
-        if b.flat is None or b.flat.dtype != dtype or b.flat.device != ref.device:
-            b.flat = torch.empty(b.numel, dtype=dtype, device=ref.device)
-        off = 0
-        for p in b.params:
-            n = p.numel()
-            if p.grad is None:
-                b.flat[off:off + n].zero_()
-            else:
-                b.flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
-        b.handle = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._materialize(b)                                 # someone may have replaced a .grad (set_to_none, clipping)
+        buf = b.flat
+        if self.comm_dtype is not None and self.comm_dtype != b.flat.dtype:
+            b.wire = b.flat.to(self.comm_dtype)
+            buf = b.wire
+        b.handle = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def wait(self) -> None:
-        """Join all transfers and write the AVERAGED gradients back (what DDP leaves in ``.grad``)."""
+        """Join all transfers; afterwards ``.grad`` holds the AVERAGED gradients (what DDP leaves there)."""
         self.reduce()
         world = dist.get_world_size(self.group)
         for b in self.buckets:
             b.handle.wait()
-            off = 0
-            for p in b.params:
-                n = p.numel()
-                avg = (b.flat[off:off + n].to(p.dtype) / world).view_as(p)
-                if p.grad is None:
-                    p.grad = avg.clone()
-                else:
-                    p.grad.copy_(avg)
-                off += n
+            if b.wire is not None:
+                b.flat.copy_(b.wire)
+                b.wire = None
+            b.flat.div_(world)
             b.handle = None
             b.pending = len(b.params)
 

@@ -209,7 +209,10 @@ class NoiseMatchingTrainer:
         return F.mse_loss(pred.float(), target)               # nn.MSELoss(reduction='mean'), drift_noise_model.py:157
 
     def step(self, x0, mu, image_context, timesteps=None):
-        self.opt.zero_grad(set_to_none=True)                  # :292
+        if self.reducer is not None:
+            self.reducer.zero_grad()                          # :292 -- gradients live in the reducer's bucket buffers
+        else:
+            self.opt.zero_grad(set_to_none=True)
         loss = self.loss(x0, mu, image_context, timesteps)
         loss.backward()                                       # :294 -- the hooks launch the bucket all-reduces
         if self.reducer is not None:
