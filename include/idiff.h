@@ -270,6 +270,44 @@ int idiff_self_attention(const void* qkv, void* out, int B, int L, int heads, fl
 int idiff_cross_vec(const float* ctx, const float* wv, const float* wo, const float* bo, float* out, int B, int D,
                     int C, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Network object: the whole model callable and the whole loop behind C entry points, for hosts that do not want
+ * to re-implement the launch plan of instancediff_b200/unet.py (csrc/unet_plan.cu).
+ *   idiff_unet_create       the network of `create_net(settings)` (models/drift_noise_model.py:142-143); the kernels
+ *                           are built for in_nc 2, out_nc 1, nf 64, ch_mult [1,2,4,4] (Configurations/config.yml:109-113)
+ *   idiff_unet_load_weight  one fp32 parameter by its state_dict name (HOST pointer; names = oracle/unet_oracle.py,
+ *                           what `load_network` hands to `load_state_dict`, models/drift_noise_model.py:706-731)
+ *   idiff_unet_finalize     packs every layer on the host (same layouts as instancediff_b200/packing.py) and uploads
+ *                           one arena; required after the last load_weight
+ *   idiff_unet_set_context  the image embedding [B][context_dim] (device): cross-attention to ONE token is
+ *                           Wo (Wv ctx) + bo for every pixel and step, computed here once per embedding
+ *   idiff_unet_forward      eps = model(x, mu, t, image_context)   utils/sde_utils.py:198; t_dev = [B] device times or
+ *                           NULL (t_scalar for the whole batch); x / mu / eps_out fp32 [B][1][H][W] device, H, W % 16 == 0
+ *   idiff_unet_reverse_sde  IRSDE.reverse_sde (utils/sde_utils.py:244-261): T x (step select, forward, fused
+ *                           Euler-Maruyama update with in-kernel Philox noise) on x IN PLACE; `table` = device copy of
+ *                           idiff_sde_pack_table's rows; stream-ordered launches (capture it in a CUDA graph per step if
+ *                           the host wants replay; the Python binding does).  Synchronises the stream once, before the
+ *                           first step, to upload the loop state.
+ * All return 0 or a negative idiff_status.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct idiff_unet idiff_unet;
+typedef struct idiff_unet_cfg {
+  int32_t in_nc, out_nc, nf, n_levels;
+  int32_t ch_mult[8];
+  int32_t context_dim, down_kernel;
+} idiff_unet_cfg;
+int idiff_unet_create(const idiff_unet_cfg* cfg, idiff_unet** out);
+void idiff_unet_destroy(idiff_unet* net);
+int idiff_unet_load_weight(idiff_unet* net, const char* name, const float* data_host, int ndim, const int64_t* shape);
+int idiff_unet_finalize(idiff_unet* net);
+int idiff_unet_set_context(idiff_unet* net, const float* ctx, int B, void* stream);
+int idiff_unet_forward(idiff_unet* net, const float* x, const float* mu, const float* t_dev, float t_scalar, float* eps_out,
+                       int B, int H, int W, void* stream);
+int idiff_unet_reverse_sde(idiff_unet* net, float* x, const float* mu, const float* table, int T, float sample_scale,
+                           uint64_t seed, uint64_t elem_offset, int B, int H, int W, void* stream);
+/* kernel launches of one forward at this shape (plan introspection) */
+int idiff_unet_num_launches(idiff_unet* net, int B, int H, int W);
+
 /* fp32 <-> bf16 / layout helpers */
 int idiff_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
 int idiff_bf16_to_f32(const void* src, float* dst, size_t n, void* stream);

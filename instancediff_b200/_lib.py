@@ -34,6 +34,13 @@ class GemmParams(C.Structure):
     ]
 
 
+class UNetCfg(C.Structure):
+    """Mirror of ``idiff_unet_cfg`` (include/idiff.h)."""
+
+    _fields_ = [("in_nc", C.c_int32), ("out_nc", C.c_int32), ("nf", C.c_int32), ("n_levels", C.c_int32),
+                ("ch_mult", C.c_int32 * 8), ("context_dim", C.c_int32), ("down_kernel", C.c_int32)]
+
+
 EPI_PLAIN, EPI_QSOFTMAX, EPI_GEGLU, EPI_LN_OUT = 0, 1, 2, 3
 
 # name -> (restype, argtypes); every symbol of include/idiff.h
@@ -82,6 +89,15 @@ SIGNATURES = {
     "idiff_linattn_fused_scratch_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "idiff_self_attention": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr]),
     "idiff_cross_vec": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr]),
+    "idiff_unet_create": (C.c_int, [C.POINTER(UNetCfg), C.POINTER(c_ptr)]),
+    "idiff_unet_destroy": (None, [c_ptr]),
+    "idiff_unet_load_weight": (C.c_int, [c_ptr, C.c_char_p, c_ptr, C.c_int, C.POINTER(C.c_int64)]),
+    "idiff_unet_finalize": (C.c_int, [c_ptr]),
+    "idiff_unet_set_context": (C.c_int, [c_ptr, c_ptr, C.c_int, c_ptr]),
+    "idiff_unet_forward": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_float, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr]),
+    "idiff_unet_reverse_sde": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_float, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
+                                         C.c_int, c_ptr]),
+    "idiff_unet_num_launches": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int]),
     "idiff_f32_to_bf16": (C.c_int, [c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "idiff_bf16_to_f32": (C.c_int, [c_ptr, c_ptr, C.c_size_t, c_ptr]),
 }

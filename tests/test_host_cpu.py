@@ -293,3 +293,15 @@ def test_shard_bounds_properties():
         sizes = [hi - lo for lo, hi in bounds]
         assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
     check()
+
+
+def test_c_level_network_object_reports_errors_without_a_gpu():
+    """idiff_unet_* (csrc/unet_plan.cu): configuration and missing-parameter errors are host-side checks."""
+    import torch
+    from instancediff_b200 import _lib
+    from instancediff_b200.native import NativeUNet
+    with pytest.raises(_lib.IdiffError, match="built for"):
+        NativeUNet(nf=32, device="cpu")
+    net = NativeUNet(device="cpu")
+    with pytest.raises(_lib.IdiffError, match="'init_conv.bias' was not loaded"):
+        net.load_state_dict({"init_conv.weight": torch.zeros(64, 2, 7, 7)})

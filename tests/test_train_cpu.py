@@ -97,8 +97,9 @@ def _rank_main(rank, world, port, sd, out_q):
     lo, hi = rank * 2, rank * 2 + 2
     ts = torch.tensor([10, 30, 60, 90]).reshape(4, 1, 1, 1)
     loss = tr.step(x0[lo:hi], mu[lo:hi], ctx[lo:hi], timesteps=ts[lo:hi])
-    out_q.put((rank, float(loss), {k: v.clone() for k, v in net.state_dict().items() if k in
-                                  ("init_conv.weight", "final_conv.bias", "mid_attn.fn.attn2.to_v.weight", "downs.1.2.fn.to_out.weight")}))
+    keys = ("init_conv.weight", "final_conv.bias", "mid_attn.fn.attn2.to_v.weight", "downs.1.2.fn.to_out.weight")
+    out_q.put((rank, float(loss), {k: v.clone() for k, v in net.state_dict().items() if k in keys},
+               {k: net.table()[k].grad.clone() for k in keys}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -138,7 +139,11 @@ def test_two_rank_step_equals_the_single_process_step_on_the_whole_batch():
     ts = torch.tensor([10, 30, 60, 90]).reshape(4, 1, 1, 1)
     loss = tr.step(x0, mu, ctx, timesteps=ts)
     assert abs(0.5 * (got[0][1] + got[1][1]) - float(loss)) < 1e-5
-    ref = net.state_dict()
     for k in got[0][2]:
-        assert torch.equal(got[0][2][k], got[1][2][k]), k                      # ranks agree bit for bit
-        assert torch.allclose(got[0][2][k], ref[k], rtol=1e-4, atol=1e-6), (k, (got[0][2][k] - ref[k]).abs().max())
+        assert torch.equal(got[0][2][k], got[1][2][k]), k                      # ranks agree bit for bit after the step
+        # averaged gradients == gradients of the whole-batch loss.  (The weights themselves are not compared across
+        # the two runs: Adam's first update is lr * g / (|g| + eps), so a rounding-level sign flip of a near-zero
+        # gradient moves a weight by 2 lr.)
+        g_ref, g_avg = net.table()[k].grad, got[0][3][k]
+        assert torch.equal(g_avg, got[1][3][k]), k
+        assert torch.allclose(g_avg, g_ref, rtol=1e-3, atol=1e-5 * g_ref.abs().max().item()), (k, (g_avg - g_ref).abs().max())
