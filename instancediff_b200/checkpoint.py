@@ -68,12 +68,17 @@ def save_network(network, network_label: str, iter_label, save_dir: str) -> str:
     return path
 
 
-def load_network(load_path: str, network, strict: bool = True, dist: bool = False, use_ema: bool = False):
+def load_network(load_path: str, network, strict: bool = True, dist: bool = False, use_ema: bool = False, key_map=None):
+    """``key_map``: optional ``f(name) -> name`` (or None to drop the tensor) applied after the reference's clean-up --
+    the hook for checkpoints whose module tree is not the App. A restatement's (the upstream network source is not in the
+    snapshot, so the real key names are unknown here)."""
     import torch
     network = getattr(network, "module", network)
-    state: Dict[str, object] = torch.load(load_path, map_location="cpu")
+    state: Dict[str, object] = torch.load(load_path, map_location="cpu", weights_only=True)   # tensors only: no pickle code
     state = clean_state_dict_keys(state, dist=dist)
     if use_ema:
         state = ema_weights(state)
+    if key_map is not None:
+        state = {nk: v for nk, v in ((key_map(k), v) for k, v in state.items()) if nk is not None}
     network.load_state_dict(state, strict=strict)
     return network
