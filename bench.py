@@ -386,7 +386,9 @@ def run_cuda(args):
     conv_traffic, traffic_src = conv_traffic_from_profile(conv_labels) if B == 32 and RES == 256 else (None, None)
     conv_algo_bytes = sum(nb for kind, _, _, _, nb in rows if kind == "conv_gemm")
     launches_per_fwd = plan.n_launch
-    gpu_launches = args.steps * (T_STEPS * (launches_per_fwd + 2) + 0)
+    # per captured step: the plan's launches minus the two time-embedding kernels (their output is a table row copied by
+    # the step-select kernel) plus step select and the fused SDE update
+    gpu_launches = args.steps * T_STEPS * (launches_per_fwd - 2 + 2)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -95,6 +95,12 @@ int idiff_philox_normal(float* out, uint64_t seed, uint64_t elem_offset, uint32_
 int idiff_step_select(const float* table, int* t_counter, float* cur_row, float* cur_time, float sample_scale,
                       void* stream);
 
+/* Same, and additionally copies row *t_counter of ss_table ([T+1][S] fp32: the `out_ss` rows of idiff_time_embed for
+ * the model times t*sample_scale, built once per sampler -- they depend on t only) to ss_out [S]: the network's time
+ * conditioning of the step without the two time-embedding launches. */
+int idiff_step_select_ss(const float* table, int* t_counter, float* cur_row, float* cur_time, float sample_scale,
+                         const float* ss_table, float* ss_out, int S, void* stream);
+
 /* Descriptor bring-up switches (bit 1: swap LBO/SBO of the MN-major V descriptor in self-attention; bit 2: swap
  * LBO/SBO of its K-major descriptors).  0 in production; no shipped test sets them. */
 int idiff_set_debug_flags(int flags);

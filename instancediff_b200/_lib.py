@@ -58,6 +58,7 @@ SIGNATURES = {
                                       C.c_uint32, C.c_size_t, C.c_size_t, c_ptr]),
     "idiff_philox_normal": (C.c_int, [c_ptr, C.c_uint64, C.c_uint64, C.c_uint32, C.c_size_t, c_ptr]),
     "idiff_step_select": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_float, c_ptr]),
+    "idiff_step_select_ss": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_float, c_ptr, c_ptr, C.c_int, c_ptr]),
     "idiff_set_debug_flags": (C.c_int, [C.c_int]),
     "idiff_debug_read_prof": (C.c_int, [c_ptr]),
     "idiff_conv_gemm": (C.c_int, [C.POINTER(GemmParams), c_ptr]),

@@ -224,6 +224,21 @@ __global__ void step_select_kernel(const float* __restrict__ table, int* __restr
   if (threadIdx.x == 0) *t_counter = t - 1;
 }
 
+// Same, plus the time conditioning of the step: row t of a [T+1][S] table (every ResBlock's scale / shift projections
+// of the time embedding, which depend on t only and are built once per sampler) is copied to `ss_out`, so the two
+// time-embedding launches leave the captured step.
+__global__ void step_select_ss_kernel(const float* __restrict__ table, int* __restrict__ t_counter,
+                                      float* __restrict__ cur_row, float* __restrict__ cur_time, float sample_scale,
+                                      const float* __restrict__ ss_table, float* __restrict__ ss_out, int S) {
+  const int t = *t_counter;
+  if (threadIdx.x < 8) cur_row[threadIdx.x] = table[(size_t)t * 8 + threadIdx.x];
+  if (threadIdx.x == 8) *cur_time = (float)t * sample_scale;
+  const float* src = ss_table + (size_t)t * S;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) ss_out[i] = src[i];
+  __syncthreads();
+  if (threadIdx.x == 0) *t_counter = t - 1;
+}
+
 static int grid_for(size_t work_items, int block) {
   size_t g = (work_items + block - 1) / block;
   const size_t cap = 148 * 8;                 // 8 resident 256-thread CTAs per SM, grid-stride beyond
@@ -309,6 +324,14 @@ int idiff_step_select(const float* table, int* t_counter, float* cur_row, float*
   IDIFF_REQUIRE(table && t_counter && cur_row && cur_time, "step_select: null pointer");
   step_select_kernel<<<1, 32, 0, as_stream(stream)>>>(table, t_counter, cur_row, cur_time, sample_scale);
   return check_launch("step_select");
+}
+
+int idiff_step_select_ss(const float* table, int* t_counter, float* cur_row, float* cur_time, float sample_scale,
+                         const float* ss_table, float* ss_out, int S, void* stream) {
+  using namespace idiff;
+  IDIFF_REQUIRE(table && t_counter && cur_row && cur_time && ss_table && ss_out && S > 0, "step_select_ss: bad arguments");
+  step_select_ss_kernel<<<1, 512, 0, as_stream(stream)>>>(table, t_counter, cur_row, cur_time, sample_scale, ss_table, ss_out, S);
+  return check_launch("step_select_ss");
 }
 
 int idiff_noise_state(float* x_out, const float* mu, const float* z, float max_sigma, int use_philox,

@@ -394,6 +394,13 @@ class IRSDE(SDE):
                       rng=torch.zeros(2, dtype=torch.int64, device=dev), graph=None,
                       z=torch.empty_like(xt) if torch_noise else None,
                       model=self.model)                 # keeps id(model) in the key unique while the entry lives
+            if hasattr(self.model, "time_table"):
+                # the network's time conditioning depends on t only: one row per step, built once per captured loop
+                # (model time of step t: float32(t) * float32(sample_scale), what idiff_step_select publishes)
+                scale32 = torch.tensor(self.sample_scale, dtype=torch.float32)
+                times = [float(torch.tensor(float(t), dtype=torch.float32) * scale32) for t in range(self._host[0].numel())]
+                st["ss_table"] = self.model.time_table(times)
+                st["ss_slot"] = self.model.time_slot(*(xt.shape[0], xt.shape[2], xt.shape[3]))
             while len(self._graph_cache) >= self.graph_cache_size:      # oldest entry first (dicts keep order)
                 self._graph_cache.pop(next(iter(self._graph_cache)))
         self._graph_cache[key] = st                                     # most recently used last
@@ -407,9 +414,15 @@ class IRSDE(SDE):
 
         def one_step():
             s = _stream(dev)
-            check(L.idiff_step_select(table.data_ptr(), st["counter"].data_ptr(), st["row"].data_ptr(),
-                                      st["time"].data_ptr(), float(self.sample_scale), s), "step_select")
-            eps = self.model.forward_into(st["x"], st["mu"], None, st["ctx"], time_ptr=st["time"].data_ptr())
+            if "ss_table" in st:
+                check(L.idiff_step_select_ss(table.data_ptr(), st["counter"].data_ptr(), st["row"].data_ptr(),
+                                             st["time"].data_ptr(), float(self.sample_scale), st["ss_table"].data_ptr(),
+                                             st["ss_slot"], st["ss_table"].shape[1], s), "step_select_ss")
+                eps = self.model.forward_into(st["x"], st["mu"], None, st["ctx"], time_ptr=st["time"].data_ptr(), ss_ready=True)
+            else:
+                check(L.idiff_step_select(table.data_ptr(), st["counter"].data_ptr(), st["row"].data_ptr(),
+                                          st["time"].data_ptr(), float(self.sample_scale), s), "step_select")
+                eps = self.model.forward_into(st["x"], st["mu"], None, st["ctx"], time_ptr=st["time"].data_ptr())
             if ode:                                     # :48-49 -- no dispersion, half the sigma^2 * score term
                 check(L.idiff_sde_step(st["x"].data_ptr(), st["x"].data_ptr(), eps.data_ptr(), st["mu"].data_ptr(), None,
                                        st["row"].data_ptr(), 2, 0, 0, 0, st["x"].numel(), s), "sde_step")

@@ -379,9 +379,30 @@ class ConditionalUNet:
             self._plans[key].bind_context(self._crossvec)
         return self._plans[key]
 
-    def forward_into(self, xt, cond, time, image_context, time_ptr: Optional[int] = None):
+    def time_table(self, times) -> torch.Tensor:
+        """[len(times), S] fp32: the time conditioning (every ResBlock's scale / shift projection of the time embedding)
+        for each model time -- it depends on t only, so a sampler builds it once and the captured step copies one row
+        (idiff_step_select_ss) instead of launching the time MLP."""
+        self._ensure_packed()
+        tm = self.pk["time"]
+        n = len(times)
+        table = torch.empty(n, self.S, dtype=torch.float32, device=self.device)
+        temb = torch.empty(1, self.td, dtype=torch.float32, device=self.device)
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        for i, t in enumerate(times):
+            check(self.L.idiff_time_embed(None, float(t), _ptr(tm["w1t"]), _ptr(tm["b1"]), _ptr(tm["w2t"]), _ptr(tm["b2"]),
+                                          _ptr(tm["wss"]), _ptr(tm["bss"]), _ptr(temb), table[i].data_ptr(), 1, self.nf, self.S, s),
+                  "time_embed")
+        return table
+
+    def time_slot(self, B, H, W) -> int:
+        """Device address of the [S] buffer the shared-time plan of this shape reads its time conditioning from."""
+        return self._plan(B, H, W, True).ss.data_ptr()
+
+    def forward_into(self, xt, cond, time, image_context, time_ptr: Optional[int] = None, ss_ready: bool = False):
         """Runs the network; returns the plan-owned fp32 output buffer [B,1,H,W] (overwritten by the
-        next call).  ``time_ptr``: device float holding the shared time (CUDA-graph replay)."""
+        next call).  ``time_ptr``: device float holding the shared time (CUDA-graph replay); ``ss_ready``: the caller
+        has already placed this step's row of ``time_table`` in ``time_slot`` (no time-embedding launches)."""
         if xt.dtype != torch.float32 or cond.dtype != torch.float32 or not xt.is_cuda:
             raise _lib.IdiffError("ConditionalUNet expects fp32 CUDA tensors [B,1,H,W]")
         B, Cx, H, W = xt.shape
@@ -407,7 +428,7 @@ class ConditionalUNet:
             shared = True
             t_scalar = float(time.reshape(-1)[0].item()) if torch.is_tensor(time) else float(time)
         plan = self._plan(B, H, W, shared)
-        plan.run(xt, cond, t_dev if time_ptr is None else time_ptr, t_scalar)
+        plan.run(xt, cond, t_dev if time_ptr is None else time_ptr, t_scalar, skip_time=ss_ready and shared)
         return plan.eps
 
     def forward(self, xt, cond, time, *unused, image_context=None, **unused_kw):
@@ -745,11 +766,12 @@ class _Plan:
                 acc[i] += e0.elapsed_time(e1)
         return [(k, lbl, fl, a / reps, nb) for (k, lbl, fl, _), a, nb in zip(calls, acc, nbytes)]
 
-    def run(self, xt, cond, t_dev, t_scalar):
+    def run(self, xt, cond, t_dev, t_scalar, skip_time=False):
         L = self.L
         s = torch.cuda.current_stream(self.dev).cuda_stream
         t_ptr = t_dev if (t_dev is None or isinstance(t_dev, int)) else t_dev.data_ptr()
-        check(L.idiff_time_embed(t_ptr, t_scalar, *self._time_args, s), "time_embed")
+        if not skip_time:
+            check(L.idiff_time_embed(t_ptr, t_scalar, *self._time_args, s), "time_embed")
         check(L.idiff_stem_conv7_tc(xt.data_ptr(), cond.data_ptr(), *self._stem_tail, s), "stem_conv7")
         for op in self.ops:
             op(s)
