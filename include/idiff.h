@@ -155,7 +155,8 @@ typedef struct idiff_gemm_params {
   const float* res0_shift;
   const float* ln_g;        /* IDIFF_EPI_LN_OUT: gain [N] */
   void* out;                /* bf16 */
-  float* gn_partial;        /* [B][idiff_conv_gemm_gn_rows(H,W)][gn_groups][2]: one row per 8x4-pixel quarter tile */
+  float* gn_partial;        /* [B][idiff_conv_gemm_gn_rows(H,W)][gn_groups][2]: one row per 8x4-pixel quarter tile; with NT < N
+                               every N tile fills the entries of its own groups (NT must be a multiple of N / 8) */
   float* out_row_stats;     /* [B*H*W][2] LayerNorm stats of the stored row (needs NT == N) */
   float qscale;             /* IDIFF_EPI_QSOFTMAX: multiplier after the softmax */
   float ln_eps;

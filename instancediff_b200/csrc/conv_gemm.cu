@@ -105,8 +105,8 @@ static int validate(const idiff_gemm_params& p) {
                     (p.src1_ld == 0 || p.src1_ld >= p.cin1), "conv_gemm: bad source pitch");
   if (p.out_row_stats) IDIFF_REQUIRE(p.NT == p.N && p.epi != IDIFF_EPI_GEGLU && p.epi != IDIFF_EPI_QSOFTMAX, "conv_gemm: out_row_stats needs NT == N");
   if (p.gn_groups > 0) {
-    IDIFF_REQUIRE(p.gn_partial && p.gn_groups == 8 && p.NT == p.N,
-                  "conv_gemm: fused GroupNorm partials need 8 groups and NT == N");
+    IDIFF_REQUIRE(p.gn_partial && p.gn_groups == 8 && p.N % 64 == 0 && p.N <= 256 && p.NT % (p.N / 8) == 0,
+                  "conv_gemm: fused GroupNorm partials need 8 groups of 8, 16 or 32 channels and NT a multiple of the group width");
     IDIFF_REQUIRE(p.epi == IDIFF_EPI_PLAIN, "conv_gemm: GroupNorm partials need the plain epilogue");
   }
   if (p.res0_scale) IDIFF_REQUIRE(p.res0 && p.res0_shift, "conv_gemm: res0 affine needs res0 and shift");

@@ -248,13 +248,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int gtid = tid & 127;
     const int r = quarter * 32 + lane, ti = r >> 3, tj = r & 7;   // accumulator row = tile pixel
     constexpr int NC = NT / 32;                                   // 32-column chunks per row
-    constexpr int CPG = NT / 8;                                   // channels per GroupNorm group (NT == N)
+    const int cpg = p.N >> 3;                                     // channels per GroupNorm group (8 groups over ALL N
+                                                                  // channels; an N tile holds NT / cpg whole groups)
     constexpr bool kTmaRes = NT == 64;
     constexpr bool kTmaOut = EPI != IDIFF_EPI_GEGLU;
     __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
     const __nv_bfloat16* res0 = reinterpret_cast<const __nv_bfloat16*>(p.res0);
     const __nv_bfloat16* res1 = reinterpret_cast<const __nv_bfloat16*>(p.res1);
-    const bool gn = p.gn_groups > 0;                              // requires NT == N: exactly 8 groups per tile
+    const bool gn = p.gn_groups > 0;                              // NT is a multiple of the group width
     const float invN = 1.f / (float)p.N;
     const int tiles_per_img = a.tiles_x * a.tiles_y;
     // per-layer column parameters staged once per CTA: [bias | wsum | ln_g], N floats each
@@ -482,12 +483,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               gl[2 * g8 + 1] = valid ? s2 : 0.f;
             }
             float tot = warp_reduce8(gl, lane);
-            if (CPG >= 16) tot += __shfl_xor_sync(0xffffffffu, tot, 8);
-            if (CPG >= 32) tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+            if (cpg >= 16) tot += __shfl_xor_sync(0xffffffffu, tot, 8);      // warp-uniform conditions
+            if (cpg >= 32) tot += __shfl_xor_sync(0xffffffffu, tot, 16);
             const int g8 = lane >> 3, st = (lane >> 2) & 1;
-            constexpr int BPG = CPG / 8;                  // 8-column blocks per group
-            if ((lane & 3) == 0 && (g8 % BPG) == 0) {
-              const int grp_idx = (cc * 32) / CPG + g8 / BPG;
+            const int bpg = cpg >> 3;                     // 8-column blocks per group: 1, 2 or 4
+            if ((lane & 3) == 0 && (g8 & (bpg - 1)) == 0) {
+              const int grp_idx = ncol0 / cpg + g8 / bpg;   // group of the GLOBAL column: N tiles fill disjoint entries
               p.gn_partial[(((size_t)b * tiles_per_img + it.tile_in_img()) * 4 + quarter) * 16 + grp_idx * 2 + st] = tot;
             }
           }

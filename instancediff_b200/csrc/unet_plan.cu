@@ -119,6 +119,7 @@ std::vector<uint16_t> pack_head_weight(const float* w /*[1][64][3][3]*/) {
 
 // ---- packed layer entries (device pointers into the arena) --------------------------------------------------------
 struct Entry {
+  std::string name;              // set for layers that may be re-packed for NT = 128 (N >= 256)
   const void* w = nullptr;       // packed bf16
   const void* w_rp = nullptr;    // row-pair packing (3x3 64 -> 64 only)
   const float* bias = nullptr;
@@ -156,6 +157,9 @@ struct Net {
   const float *w1t = nullptr, *b1 = nullptr, *w2t = nullptr, *b2 = nullptr, *wss = nullptr, *bss = nullptr;
   std::map<std::vector<int>, std::unique_ptr<Plan>> plans;  // key {B, H, W, shared_time}
   std::map<int, std::vector<float*>> crossvec;              // per batch size: [3 layers][B][C]
+  std::map<std::string, void*> variants;                    // "<layer>:<NT>" -> weights packed for another N tile
+  std::map<std::string, std::vector<float>> variant_src;    // fp32 weights (after LayerNorm folding) of those layers
+  const void* packed_variant(const std::string& name, int NT, int N, int cin, int k);
   int n_levels() const { return (int)dims.size() - 1; }
   std::vector<std::string> spatial_layers() const {
     return {"downs." + std::to_string(n_levels() - 1) + ".2", "mid_attn", "ups.0.2"};
@@ -255,6 +259,14 @@ struct Plan {
     p->out_row_stats = o.out_stats;
     p->qscale = o.qscale; p->ln_eps = o.ln_eps;
     if (o.bias_img_slot) ctx_slots[o.bias_img_slot] = p;
+    // small grids: split a 256-wide N tile in two (same rule and same bit-identical results as unet.py::_Plan.gemm)
+    if (o.NT < 0 && p->NT == 256 && !e.name.empty() && !o.w_override && o.epi == IDIFF_EPI_PLAIN && !o.res0 && !o.res1 && !o.out_stats) {
+      const int tiles = B * ((out.H + 15) / 16) * ((out.W + 7) / 8);
+      if (tiles * (p->N / 256) <= 111) {
+        const void* v = net->packed_variant(e.name, 128, e.N, e.cin, e.k);
+        if (v) { p->NT = 128; p->w = v; }
+      }
+    }
     const bool rp = !o.w_override && rowpair_ok(e, src1, out, o.k, o.stride, o.up) && idiff_conv3_rowpair_supported(p);
     if (rp) {
       p->w = e.w_rp;
@@ -483,8 +495,23 @@ struct Plan {
   }
 };
 
+const void* Net::packed_variant(const std::string& name, int NT, int N, int cin, int k) {
+  const std::string key = name + ":" + std::to_string(NT);
+  auto it = variants.find(key);
+  if (it != variants.end()) return it->second;
+  auto src = variant_src.find(name);
+  if (src == variant_src.end()) return nullptr;
+  const std::vector<uint16_t> pk = pack_conv_weight(src->second.data(), N, cin, k, NT);
+  void* dev = nullptr;
+  if (cudaMalloc(&dev, pk.size() * 2) != cudaSuccess || cudaMemcpy(dev, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess)
+    return nullptr;
+  variants[key] = dev;
+  return dev;
+}
+
 Net::~Net() {
   plans.clear();
+  for (auto& kv : variants) cudaFree(kv.second);
   for (auto& kv : crossvec)
     for (float* p : kv.second) cudaFree(p);
   if (arena) cudaFree(arena);
@@ -515,6 +542,9 @@ int finalize(Net* net) {
   };
   ArenaBuilder ab;
   std::string missing;
+  for (auto& kv : net->variants) cudaFree(kv.second);        // re-finalize: packings of the previous weights
+  net->variants.clear();
+  net->variant_src.clear();
   auto get = [&](const std::string& k) -> const HostT& {
     static const HostT empty;
     const HostT* t = need(k);
@@ -527,6 +557,7 @@ int finalize(Net* net) {
     const std::vector<float>& w = w_over ? *w_over : get(name + ".weight").v;
     if (w.size() != (size_t)N * cin * k * k) return;
     ab.add(pack_conv_weight(w.data(), N, cin, k, NT), &e.w);
+    if (N >= 256) { e.name = name; net->variant_src[name] = w; }
     if (N == 64 && cin == 64 && k == 3) ab.add(pack_conv3_rowpair(w.data()), &e.w_rp);
     if (b_over) ab.addf(*b_over, &e.bias);
     else if (need(name + ".bias")) ab.addf(get(name + ".bias").v, &e.bias);

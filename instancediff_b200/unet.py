@@ -206,6 +206,8 @@ class ConditionalUNet:
         """The weights changed: drop the packed arena and every launch plan.  Packing itself is deferred to the first
         forward, so ``ConditionalUNet(...).load_state_dict(sd)`` packs once, not twice."""
         self.pk = None
+        self._variants: Dict[tuple, torch.Tensor] = {}
+        self._variant_src: Dict[str, torch.Tensor] = {}
         self._plans.clear()
         self._ctx_key = None
         self._version += 1                          # captured graphs hold pointers into the old packing
@@ -213,6 +215,15 @@ class ConditionalUNet:
     def _ensure_packed(self):
         if self.pk is None:
             self._pack()
+
+    def packed_variant(self, name: str, NT: int) -> torch.Tensor:
+        """The weights of layer ``name`` packed for another N tile than the default one (small grids: a 256-channel
+        layer with fewer work items than SMs runs as two 128-channel tiles).  Packed on the host on first use."""
+        key = (name, NT)
+        if key not in self._variants:
+            w = self._variant_src[name]
+            self._variants[key] = pack_conv_weight(w, NT).to(self.device)
+        return self._variants[key]
 
     def _pack(self):
         """Host-side packing: every layout transform runs on CPU copies of the parameters, the results are laid out
@@ -232,6 +243,9 @@ class ConditionalUNet:
                             cin=w.shape[1], k=(w.shape[2] if w.dim() == 4 else 1) if k is None else k)
             if tuple(w.shape) == (64, 64, 3, 3):          # second packing for idiff_conv3_rowpair
                 pk[name]["w_rp"] = pack_conv3_rowpair(w)
+            if N >= 256:                                   # may be re-packed for NT = 128 (small grids)
+                pk[name]["name"] = name
+                self._variant_src[name] = w.detach().clone()
             return pk[name]
 
         def resblock(prefix):
@@ -495,6 +509,16 @@ class _Plan:
         p.src0_ld, p.src1_ld = src0_ld, 0
         p.N = entry["N"]
         p.NT = entry["NT"] if NT is None else NT
+        # Small grids: with fewer (pixel tile x N tile) items than ~3/4 of the SMs, a 256-wide N tile is split in two.
+        # An M128 x N128 MMA takes about half the time of an N256 one, so the layer's critical path halves while the
+        # idle SMs take the extra items (N = 64 would not help: its MMAs are bound by the A-operand read).  Results
+        # are bit-identical: every output element sees the same K sequence, GroupNorm entries are per group.
+        if (NT is None and p.NT == 256 and "name" in entry and w_override is None and epi == EPI_PLAIN
+                and res0 is None and res1 is None and out_stats is None):
+            tiles = self.B * (-(-out.H // TILE_H)) * (-(-out.W // TILE_W))
+            if tiles * (p.N // 256) <= 111:
+                p.NT = 128
+                w_override = self.net.packed_variant(entry["name"], 128)
         p.a_silu, p.epi = a_silu, epi
         p.gn_groups = GN_GROUPS if gn_partial is not None else 0
         p.out_ld = out.C if out_ld is None else out_ld

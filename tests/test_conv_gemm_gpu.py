@@ -210,6 +210,23 @@ def test_groupnorm_partials():
     assert rel_err(y, gn) <= 1e-3, describe(y, gn, "gn")
 
 
+@pytest.mark.parametrize("N,NT", [(256, 128), (256, 64), (128, 64)])
+def test_groupnorm_partials_with_a_split_n_tile(N, NT):
+    """NT < N (small grids split a wide N tile): every N tile fills the entries of its own groups; output and partial
+    sums are BIT-identical to the single-tile run (same K sequence per element, same per-group reduction)."""
+    from instancediff_b200 import _lib
+    B, H, W = 2, 32, 24
+    rows = _lib.lib().idiff_conv_gemm_gn_rows(H, W)
+    part_a = torch.full((B, rows, 8, 2), float("nan"), device="cuda")
+    part_b = torch.full((B, rows, 8, 2), float("nan"), device="cuda")
+    out_a, ref, _ = _run(B, H, W, 128, 0, N, 3, seed=4, gn_groups=8, gn_partial=part_a)
+    out_b, _, _ = _run(B, H, W, 128, 0, N, 3, seed=4, NT=NT, gn_groups=8, gn_partial=part_b)
+    assert torch.equal(out_a, out_b) and rel_err(out_b, ref) <= TOL
+    assert not torch.isnan(part_b).any() and torch.equal(part_a, part_b)
+    r = ref.reshape(B, H * W, 8, N // 8)
+    assert torch.allclose(part_b.sum(dim=1)[..., 0], r.sum(dim=(1, 3)), rtol=1e-3, atol=1e-2)
+
+
 def test_layernorm_fold_and_row_stats():
     """acc' = (acc - mean*wsum)*rstd (+bias) equals Linear(LayerNorm(x)); out_row_stats are the LN stats."""
     from instancediff_b200 import ops
