@@ -98,8 +98,10 @@ def _rank_main(rank, world, port, sd, out_q):
     ts = torch.tensor([10, 30, 60, 90]).reshape(4, 1, 1, 1)
     loss = tr.step(x0[lo:hi], mu[lo:hi], ctx[lo:hi], timesteps=ts[lo:hi])
     keys = ("init_conv.weight", "final_conv.bias", "mid_attn.fn.attn2.to_v.weight", "downs.1.2.fn.to_out.weight")
-    out_q.put((rank, float(loss), {k: v.clone() for k, v in net.state_dict().items() if k in keys},
-               {k: net.table()[k].grad.clone() for k in keys}))
+    # numpy arrays travel through the queue BY VALUE (torch tensors are passed as shared-memory handles that die with
+    # this process -- the parent may read them after the rank has exited)
+    out_q.put((rank, float(loss), {k: v.numpy().copy() for k, v in net.state_dict().items() if k in keys},
+               {k: net.table()[k].grad.numpy().copy() for k in keys}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -120,6 +122,7 @@ def test_two_rank_step_equals_the_single_process_step_on_the_whole_batch():
         p.join(timeout=60)
         assert p.exitcode == 0
     got.sort(key=lambda g: g[0])
+    got = [(r, l, {k: torch.from_numpy(v) for k, v in w.items()}, {k: torch.from_numpy(v) for k, v in gr.items()}) for r, l, w, gr in got]
 
     # single process, whole batch, SAME per-sample noise: rank r drew its noise from generator 100 + r
     class _Joined(_CpuStates):

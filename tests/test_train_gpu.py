@@ -77,7 +77,7 @@ def _nccl_rank(rank, world, port, sd, q):
     ts = torch.tensor([10, 30, 60, 90]).reshape(4, 1, 1, 1)
     lo = rank * 2
     loss = tr.step(x0[lo:lo + 2], mu[lo:lo + 2], ctx[lo:lo + 2], timesteps=ts[lo:lo + 2])
-    q.put((rank, float(loss), {k: v.cpu() for k, v in net.state_dict().items() if k in ("init_conv.weight", "final_conv.bias")}))
+    q.put((rank, float(loss), {k: v.cpu().numpy().copy() for k, v in net.state_dict().items() if k in ("init_conv.weight", "final_conv.bias")}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -99,5 +99,6 @@ def test_two_gpu_nccl_step_keeps_the_ranks_identical():
         p.join(timeout=60)
         assert p.exitcode == 0
     for k in got[0][2]:
-        assert torch.equal(got[0][2][k], got[1][2][k]), k
-        assert not torch.equal(got[0][2][k], sd[k])
+        a, b = torch.from_numpy(got[0][2][k]), torch.from_numpy(got[1][2][k])
+        assert torch.equal(a, b), k
+        assert not torch.equal(a, sd[k])
