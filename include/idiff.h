@@ -122,6 +122,29 @@ int idiff_debug_read_prof(unsigned long long* out16_host);
  * TMA copies through 128B-swizzled staging tiles.
  * Built combinations: 3x3 {no transform | affine+SiLU}, 4x4/s2 {no transform}, 1x1 {any transform};
  * QSOFTMAX needs NT == 128, GEGLU NT == 256, LN_OUT NT == N; anything else -> IDIFF_ERR_UNSUPPORTED. */
+
+/* GroupNorm finalize folded into the producing kernel (csrc/gn_fuse.cuh) instead of a separate idiff_gn_finalize
+ * launch: the epilogue adds its (sum, sum of squares) per warp tile as 64-bit fixed-point integers (exact, so the
+ * totals are independent of order, grid and batch sharding) into `sums`, and the last CTA to finish writes
+ *   scale = rstd*gamma*(1+ts), shift = (beta - mean*rstd*gamma)*(1+ts) + tb      (ts/tb may be NULL)
+ * for every (image, channel) and zeroes `sums` / `arrivals` again.  Both must be ZERO before the first launch
+ * (cudaMemset once); one pair can serve every layer of a stream-ordered plan.  This struct lives in HOST memory. */
+#define IDIFF_GN_SLOTS 16
+typedef struct idiff_gn_fuse {
+  void* sums;               /* device, int64 [B][IDIFF_GN_SLOTS][groups][2], 16-byte aligned */
+  unsigned int* arrivals;   /* device, one counter */
+  const float* gamma;       /* [N] */
+  const float* beta;        /* [N] */
+  const float* t_scale;     /* [B or 1][t_ld]: time-embedding scale / shift rows, or NULL */
+  const float* t_shift;
+  float* scale_out;         /* [B][N] */
+  float* shift_out;         /* [B][N] */
+  int32_t t_ld;             /* row pitch of t_scale / t_shift (0 = one row shared by the batch) */
+  int32_t count_per_group;  /* H*W*(N/groups) */
+  float eps;
+  int32_t reserved;
+} idiff_gn_fuse;
+
 typedef struct idiff_gemm_params {
   /* geometry (OUTPUT grid) */
   int32_t B, H, W;          /* output pixels */
@@ -133,7 +156,7 @@ typedef struct idiff_gemm_params {
   int32_t NT;               /* N tile: 64, 128 or 256; N % NT == 0 */
   int32_t a_silu;           /* apply SiLU after the A affine */
   int32_t epi;              /* IDIFF_EPI_* */
-  int32_t gn_groups;        /* >0: write GroupNorm partial sums (requires gn_partial) */
+  int32_t gn_groups;        /* >0: GroupNorm statistics of the output (requires gn_partial or gn_fuse) */
   int32_t out_ld;           /* leading dimension (elements) of out */
   int32_t dbg_swap_lbo_sbo; /* bring-up switch used by the probe test only */
   int32_t src0_ld;          /* pixel pitch (elements) of src0 / src1; 0 = cin0 / cin1 */
@@ -160,6 +183,8 @@ typedef struct idiff_gemm_params {
   float* out_row_stats;     /* [B*H*W][2] LayerNorm stats of the stored row (needs NT == N) */
   float qscale;             /* IDIFF_EPI_QSOFTMAX: multiplier after the softmax */
   float ln_eps;
+  const idiff_gn_fuse* gn_fuse; /* HOST pointer or NULL.  With gn_groups > 0: fold the GroupNorm finalize into this launch
+                               (gn_partial is then not written and may be NULL) */
 } idiff_gemm_params;
 
 enum {
@@ -172,6 +197,7 @@ enum {
 int idiff_conv_gemm(const idiff_gemm_params* p, void* stream);
 /* sizeof(idiff_gemm_params) as compiled -- lets a binding verify its struct mirror */
 int idiff_sizeof_gemm_params(void);
+int idiff_sizeof_gn_fuse(void);
 /* shared memory the kernel will request for these params (bytes), or negative status */
 int idiff_conv_gemm_smem_bytes(const idiff_gemm_params* p);
 /* rows of GroupNorm partial sums idiff_conv_gemm writes per image for an H x W output (the `ntile`
@@ -246,6 +272,12 @@ int idiff_add_rows(const void* a, const void* b, void* out, float* out_row_stats
 
 /* y = LayerNorm_c(x) * g  (channel LayerNorm, gain only) materialised in bf16. */
 int idiff_chan_ln(const void* x, const float* g, void* y, float eps, size_t rows, int C, void* stream);
+
+/* idiff_chan_ln + idiff_gn_stats + idiff_gn_finalize in one launch (entry of the SpatialTransformer): y = ChanLN(x)*g
+ * in bf16, GroupNorm(G groups) statistics of the rounded y accumulated as exact integers, affine written by the last
+ * CTA (see idiff_gn_fuse).  H*W must be a multiple of 2048 / C. */
+int idiff_chan_ln_gn(const void* x, const float* g, void* y, float ln_eps, int B, int HW, int C, int G,
+                     const idiff_gn_fuse* fuse, void* stream);
 
 /* Linear attention context.  qkv: bf16 [B][HW][384] (q already soft-maxed by the GEMM epilogue).
  * Computes ctx[b,h,d,e] = sum_n softmax_n(k)[d,n] v[e,n] / HW, then the per-image effective output

@@ -15,6 +15,19 @@ c_f32p = C.c_void_p      # device pointers travel as integers (tensor.data_ptr()
 c_ptr = C.c_void_p
 
 
+GN_SLOTS = 16            # IDIFF_GN_SLOTS
+
+
+class GnFuse(C.Structure):
+    """Mirror of ``idiff_gn_fuse`` (include/idiff.h): GroupNorm finalize folded into the producing launch."""
+
+    _fields_ = [
+        ("sums", c_ptr), ("arrivals", c_ptr), ("gamma", c_ptr), ("beta", c_ptr), ("t_scale", c_ptr), ("t_shift", c_ptr),
+        ("scale_out", c_ptr), ("shift_out", c_ptr),
+        ("t_ld", C.c_int32), ("count_per_group", C.c_int32), ("eps", C.c_float), ("reserved", C.c_int32),
+    ]
+
+
 class GemmParams(C.Structure):
     """Mirror of ``idiff_gemm_params`` (include/idiff.h)."""
 
@@ -31,6 +44,7 @@ class GemmParams(C.Structure):
         ("res0", c_ptr), ("res1", c_ptr), ("res0_scale", c_ptr), ("res0_shift", c_ptr),
         ("ln_g", c_ptr), ("out", c_ptr), ("gn_partial", c_ptr), ("out_row_stats", c_ptr),
         ("qscale", C.c_float), ("ln_eps", C.c_float),
+        ("gn_fuse", C.POINTER(GnFuse)),
     ]
 
 
@@ -83,6 +97,9 @@ SIGNATURES = {
                                    C.c_int, c_ptr]),
     "idiff_add_rows": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_float, C.c_size_t, C.c_int, c_ptr]),
     "idiff_chan_ln": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_float, C.c_size_t, C.c_int, c_ptr]),
+    "idiff_chan_ln_gn": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(GnFuse),
+                                   c_ptr]),
+    "idiff_sizeof_gn_fuse": (C.c_int, []),
     "idiff_linattn_context": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr]),
     "idiff_linattn_scratch_floats": (C.c_size_t, [C.c_int, C.c_int]),
     "idiff_linattn_fused": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
@@ -126,6 +143,8 @@ def lib() -> C.CDLL:
             fn.argtypes = args
         if handle.idiff_sizeof_gemm_params() != C.sizeof(GemmParams):
             raise IdiffError("idiff_gemm_params layout mismatch between include/idiff.h and _lib.GemmParams")
+        if handle.idiff_sizeof_gn_fuse() != C.sizeof(GnFuse):
+            raise IdiffError("idiff_gn_fuse layout mismatch between include/idiff.h and _lib.GnFuse")
         _lib = handle
     return _lib
 

@@ -23,6 +23,7 @@ extern "C" {
 int idiff_abi_version(void) { return 1; }
 
 int idiff_sizeof_gemm_params(void) { return (int)sizeof(idiff_gemm_params); }
+int idiff_sizeof_gn_fuse(void) { return (int)sizeof(idiff_gn_fuse); }
 
 const char* idiff_last_error(void) { return idiff::g_err; }
 

@@ -255,6 +255,24 @@ IDIFF_DEVINL float silu_fast(float x) {       // x * sigmoid(x) = 0.5 x (1 + tan
   return fmaf(h, tanh_fast(h), h);
 }
 IDIFF_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU for hot epilogues: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of
+// the stored product): 2 MUFU + ~13 FMA-pipe instructions instead of erff's ~40 with two branches.
+IDIFF_DEVINL float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);                // erf(|x| / sqrt 2)
+  const float h = 0.5f * x;
+  return fmaf(fabsf(h), erf_abs, h);                         // 0.5 x (1 + sign(x) erf_abs)
+}
+IDIFF_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 IDIFF_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);

@@ -62,6 +62,7 @@ struct RpArgs {
   const float* bias;          // [64] or nullptr
   float* gn_partial;          // [B][H * nstrips * 4][8][2] or nullptr
   int B, H, W, nstrips, rows2, total_items;
+  GnFuse gf;                  // fused GroupNorm finalize (gf.sums != nullptr: no partial rows)
   unsigned long long* prof;   // 16 role counters of CTA 0 (-DIDIFF_PROF builds, params.reserved0 = 1) or nullptr:
                               //  0 kernel cycles  1 items  2 ld: wait empty  3 ld: issue loads  4 ld: data + store
                               //  5 mma: wait tmem  6 mma: wait upper pair  7 mma: wait lower pair  8 mma: issue
@@ -192,7 +193,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_rowpair_kernel(const __grid
           const float tot = warp_reduce16(gl, lane);              // lane L: value L >> 1 = group*2 + {sum, sumsq}
           if ((lane & 1) == 0) {
             const int prow = ((y0 + orow) * a.nstrips + sx) * 4 + quarter;
-            a.gn_partial[((size_t)b * rows_per_img + prow) * 16 + (lane >> 1)] = tot;
+            if (a.gf.sums) gn_fuse_add(a.gf, b, prow, lane >> 1, tot);
+            else a.gn_partial[((size_t)b * rows_per_img + prow) * 16 + (lane >> 1)] = tot;
           }
         }
         uint4 pk[8];
@@ -216,6 +218,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3_rowpair_kernel(const __grid
       while (i >= a.rows2) { i -= a.rows2; ++strip; }
     }
     if (lane == 0) bulk_wait_all();
+    if (GN && a.gf.sums)                                          // last CTA of the grid: sums -> affine of the next layer
+      gn_fuse_finish<kEpiThreads>(a.gf, reinterpret_cast<float2*>(smem + RP_OFF_OUT), reinterpret_cast<volatile int*>(smem + kHeader - 16),
+                                  tid, 3, kEpiWarps * kStageTile / 8);
     if (prof && tid == 0) { a.prof[9] = pacc9; a.prof[10] = pacc10; a.prof[1] = g1 - g0; }
   } else if (warp < kWarpB) {
     // ============================== loaders ===================================================
@@ -510,7 +515,7 @@ int idiff_conv3_rowpair(const idiff_gemm_params* p, void* stream) {
   IDIFF_REQUIRE((p->a_scale == nullptr) == (p->a_shift == nullptr), "conv3_rowpair: a_scale/a_shift must come together");
   IDIFF_REQUIRE(aligned16(p->src0) && aligned16(p->w) && aligned16(p->out), "conv3_rowpair: 16 B alignment");
   IDIFF_REQUIRE(p->out_ld >= 64 && p->out_ld % 8 == 0, "conv3_rowpair: bad out_ld");
-  IDIFF_REQUIRE(p->gn_groups == 0 || (p->gn_groups == 8 && p->gn_partial), "conv3_rowpair: GroupNorm partials need 8 groups");
+  IDIFF_REQUIRE(p->gn_groups == 0 || (p->gn_groups == 8 && (p->gn_partial || p->gn_fuse)), "conv3_rowpair: GroupNorm partials need 8 groups");
   RpArgs a;
   a.src = reinterpret_cast<const uint8_t*>(p->src0);
   a.a_scale = p->a_scale;
@@ -518,6 +523,7 @@ int idiff_conv3_rowpair(const idiff_gemm_params* p, void* stream) {
   a.w = reinterpret_cast<const uint8_t*>(p->w);
   a.bias = p->bias;
   a.gn_partial = p->gn_groups ? p->gn_partial : nullptr;
+  IDIFF_REQUIRE(gn_fuse_make(a.gf, p->gn_groups ? p->gn_fuse : nullptr, p->B, 64, 8), "conv3_rowpair: incomplete gn_fuse description");
   a.B = p->B; a.H = p->H; a.W = p->W;
   a.nstrips = (p->W + RP_W - 1) / RP_W;
   a.rows2 = p->H / 2;
@@ -535,7 +541,7 @@ int idiff_conv3_rowpair(const idiff_gemm_params* p, void* stream) {
   cudaError_t e = per_device_setup(once, &num_sms, [] { return cudaSuccess; });
   if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "conv3_rowpair setup: %s", cudaGetErrorString(e));
   const int grid = a.total_items < num_sms ? a.total_items : num_sms;
-  const bool gn = a.gn_partial != nullptr;
+  const bool gn = a.gn_partial != nullptr || a.gf.sums != nullptr;
   if (p->a_scale && (p->a_silu & 2))          // a_silu bit 1: evaluate affine + SiLU in packed bf16x2
     e = gn ? launch_rp<AMODE_AFFINE_SILU_PK, true>(a, grid, as_stream(stream)) : launch_rp<AMODE_AFFINE_SILU_PK, false>(a, grid, as_stream(stream));
   else if (p->a_scale) e = gn ? launch_rp<AMODE_AFFINE_SILU, true>(a, grid, as_stream(stream)) : launch_rp<AMODE_AFFINE_SILU, false>(a, grid, as_stream(stream));

@@ -105,7 +105,7 @@ static int validate(const idiff_gemm_params& p) {
                     (p.src1_ld == 0 || p.src1_ld >= p.cin1), "conv_gemm: bad source pitch");
   if (p.out_row_stats) IDIFF_REQUIRE(p.NT == p.N && p.epi != IDIFF_EPI_GEGLU && p.epi != IDIFF_EPI_QSOFTMAX, "conv_gemm: out_row_stats needs NT == N");
   if (p.gn_groups > 0) {
-    IDIFF_REQUIRE(p.gn_partial && p.gn_groups == 8 && p.N % 64 == 0 && p.N <= 256 && p.NT % (p.N / 8) == 0,
+    IDIFF_REQUIRE((p.gn_partial || p.gn_fuse) && p.gn_groups == 8 && p.N % 64 == 0 && p.N <= 256 && p.NT % (p.N / 8) == 0,
                   "conv_gemm: fused GroupNorm partials need 8 groups of 8, 16 or 32 channels and NT a multiple of the group width");
     IDIFF_REQUIRE(p.epi == IDIFF_EPI_PLAIN, "conv_gemm: GroupNorm partials need the plain epilogue");
   }
@@ -205,6 +205,8 @@ int idiff_conv_gemm(const idiff_gemm_params* pp, void* stream) {
   a.ntiles_n = pp->N / pp->NT;
   a.total_items = a.tiles_x * a.tiles_y * pp->B * a.ntiles_n;
   a.prof = nullptr;
+  IDIFF_REQUIRE(gn_fuse_make(a.gf, pp->gn_groups > 0 ? pp->gn_fuse : nullptr, pp->B, pp->N, 8),
+                "conv_gemm: incomplete gn_fuse description");
   IDIFF_REQUIRE(s.total <= kSmemLimit && s.SA >= 1, "conv_gemm: shared memory plan %d B too large", s.total);
 #ifdef IDIFF_PROF
   if (pp->reserved0) {

@@ -28,6 +28,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "gn_fuse.cuh"
 #include "host_common.h"
 
 namespace idiff {
@@ -71,6 +72,7 @@ struct KArgs {
   int res_nbuf;                       // residual staging sets per warp: 2 = the next item's tiles are prefetched
   int tiles_x, tiles_y, ntiles_n, total_items;
   unsigned long long* prof;           // 16 counters of CTA 0 (IDIFF_PROF builds), or nullptr
+  GnFuse gf;                          // fused GroupNorm finalize (gf.sums == nullptr: partial rows are written instead)
   alignas(64) CUtensorMap tm_out;     // [B][H][W][out cols] bf16, box {64, 8, 4, 1}, 128B swizzle
   alignas(64) CUtensorMap tm_res0;    // residuals (NT == 64 only), same box
   alignas(64) CUtensorMap tm_res1;
@@ -294,6 +296,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     ItemIter it;
     it.init(a, blockIdx.x + grp * gridDim.x, 2 * gridDim.x);      // this group's items: every second one of the CTA
     if (res_tma && res_pref && it.valid()) issue_residuals(it, 0);
+    // Residual rows read straight from global memory (NT > 64: no room for TMA staging tiles) are pulled into L2 one
+    // item ahead -- the epilogue's loads are synchronous (load -> use), so an HBM miss per 32-column chunk was ~1 us of
+    // exposed latency per chunk and group.
+    const bool res_l2 = !kTmaRes && (res0 || res1);
+    auto prefetch_residuals = [&](const ItemIter& ri) {
+      const int oy2 = ri.oy0() + ti, ox2 = ri.ox0() + tj;
+      if (oy2 < p.H && ox2 < p.W) {
+        const size_t e2 = (((size_t)ri.b * p.H + oy2) * p.W + ox2) * p.N + ri.nt * NT;
+#pragma unroll
+        for (int l = 0; l < NT / 64; ++l) {
+          if (res0) prefetch_l2(res0 + e2 + l * 64);
+          if (res1) prefetch_l2(res1 + e2 + l * 64);
+        }
+      }
+    };
+    if (res_l2 && it.valid()) prefetch_residuals(it);
     for (; it.valid(); it.next()) {
       const int b = it.b, n0 = it.nt * NT;
       const int oy = it.oy0() + ti, ox = it.ox0() + tj;
@@ -313,6 +331,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         } else {
           issue_residuals(it, 0);
         }
+      }
+      if (res_l2) {
+        ItemIter nx = it;
+        nx.next();
+        if (nx.valid()) prefetch_residuals(nx);
       }
       float mean_in = 0.f, rstd_in = 1.f;
       if (p.row_stats) {
@@ -489,7 +512,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int bpg = cpg >> 3;                     // 8-column blocks per group: 1, 2 or 4
             if ((lane & 3) == 0 && (g8 & (bpg - 1)) == 0) {
               const int grp_idx = ncol0 / cpg + g8 / bpg;   // group of the GLOBAL column: N tiles fill disjoint entries
-              p.gn_partial[(((size_t)b * tiles_per_img + it.tile_in_img()) * 4 + quarter) * 16 + grp_idx * 2 + st] = tot;
+              if (a.gf.sums) gn_fuse_add(a.gf, b, it.tile_in_img() * 4 + quarter, grp_idx * 2 + st, tot);
+              else p.gn_partial[(((size_t)b * tiles_per_img + it.tile_in_img()) * 4 + quarter) * 16 + grp_idx * 2 + st] = tot;
             }
           }
 
@@ -508,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           } else if (EPI == IDIFF_EPI_GEGLU) {
             float o[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) o[q] = v[2 * q] * gelu_erf(v[2 * q + 1]);
+            for (int q = 0; q < 16; ++q) o[q] = v[2 * q] * gelu_erf_fast(v[2 * q + 1]);
             if (valid) {
               uint4* dst = reinterpret_cast<uint4*>(outp + m * p.out_ld + (ncol0 >> 1));
               dst[0] = pack_bf16x8(o);
@@ -532,6 +556,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       if (grp == 0) PROF_ADD(10, tp);
     }
     if (kTmaOut && lane == 0) bulk_wait_all();              // staging tiles must outlive the last TMA store
+    if (EPI == IDIFF_EPI_PLAIN && a.gf.sums)                // last CTA of the grid: sums -> affine of the next layer
+      gn_fuse_finish<kEpiThreads>(a.gf, reinterpret_cast<float2*>(smem + a.offOut), reinterpret_cast<volatile int*>(smem + kHeader - 16),
+                                  tid, 3, kEpiWarps * a.nbuf_out * kStageTile / 8);
     if (prof && tid == 0) { a.prof[9] = pacc9; a.prof[10] = pacc10; a.prof[1] = mine; }
   } else if (warp < kWarpB) {
     // ============================== A producers ==============================================

@@ -3,6 +3,7 @@
 // thread = 8 bf16 channels), coalesced along the channel-last axis, warp-shuffle reductions.
 // Spec: SURVEY.md App. A (ResBlock / PreNorm / time MLP); serves utils/sde_utils.py:198.
 #include "common.cuh"
+#include "gn_fuse.cuh"
 #include "host_common.h"
 
 namespace idiff {
@@ -182,6 +183,55 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ parti
     dst[0] = a1;
     dst[1] = a2;
   }
+}
+
+// ---- channel LayerNorm + GroupNorm statistics + GroupNorm finalize in ONE launch (SpatialTransformer entry) ------
+// y = ChanLN(x) * gain (bf16, what idiff_chan_ln writes); the GroupNorm sums are taken over the ROUNDED y (what
+// idiff_gn_stats would read back) and finished by the last CTA (gn_fuse.cuh).  grid = (ntile, B), block = 256.
+__global__ void __launch_bounds__(256)
+chan_ln_gn_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gain, __nv_bfloat16* __restrict__ y,
+                  float ln_eps, int HW, int C, const GnFuse gf) {
+  __shared__ float red[256][2];
+  __shared__ float2 stat[1024];
+  __shared__ int flag;
+  const int b = blockIdx.y, tile = blockIdx.x;
+  const int lpr = C >> 3, rows_per_sweep = 256 / lpr;
+  const int c8 = threadIdx.x % lpr, roff = threadIdx.x / lpr;
+  const int r_end = min(HW, (tile + 1) * GN_TILE_ROWS);
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gain + c8 * 8));
+  const float4 g1 = __ldg(reinterpret_cast<const float4*>(gain + c8 * 8 + 4));
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  float a1 = 0.f, a2 = 0.f;
+  // HW % rows_per_sweep == 0 is required by the launcher: the lanes of a row stay converged for the shuffles
+  for (int r = tile * GN_TILE_ROWS + roff; r < r_end; r += rows_per_sweep) {
+    const size_t off = ((size_t)b * HW + r) * C + c8 * 8;
+    float f[8];
+    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(x + off)), f);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s1 += f[e]; s2 += f[e] * f[e]; }
+    row_reduce(s1, s2, lpr);
+    const float mean = s1 / C, var = fmaxf(s2 / C - mean * mean, 0.f), rstd = rsqrtf(var + ln_eps);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = (f[e] - mean) * rstd * gg[e];
+    const uint4 q = pack_bf16x8(f);
+    *reinterpret_cast<uint4*>(y + off) = q;
+    unpack_bf16x8(q, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { a1 += f[e]; a2 += f[e] * f[e]; }
+  }
+  red[threadIdx.x][0] = a1;
+  red[threadIdx.x][1] = a2;
+  __syncthreads();
+  const int vpg = (C / gf.G) >> 3;                            // 8-channel vectors per group
+  if (threadIdx.x < 2 * gf.G) {
+    const int g = threadIdx.x >> 1, st = threadIdx.x & 1;
+    float t = 0.f;
+    for (int ro = 0; ro < rows_per_sweep; ++ro)
+      for (int v = 0; v < vpg; ++v) t += red[ro * lpr + g * vpg + v][st];
+    gn_fuse_add(gf, b, tile, g * 2 + st, t);
+  }
+  gn_fuse_finish<256>(gf, stat, &flag, threadIdx.x, 1, 1024);
 }
 
 // ---- GroupNorm finalize: partial sums -> per-(image,channel) affine (with time modulation) -------
@@ -393,6 +443,20 @@ int idiff_chan_ln(const void* x, const float* g, void* y, float eps, size_t rows
 }
 
 int idiff_gn_stats_ntile(int HW) { return (HW + GN_TILE_ROWS - 1) / GN_TILE_ROWS; }
+
+int idiff_chan_ln_gn(const void* x, const float* g, void* y, float ln_eps, int B, int HW, int C, int G,
+                     const idiff_gn_fuse* fuse, void* stream) {
+  IDIFF_REQUIRE(x && g && y && fuse && B > 0 && HW > 0, "chan_ln_gn: bad arguments");
+  if (int rc = check_c(C, "chan_ln_gn")) return rc;
+  IDIFF_REQUIRE(G > 0 && G <= 128 && C % G == 0 && (C / G) % 8 == 0, "chan_ln_gn: unsupported groups %d", G);
+  IDIFF_REQUIRE(HW % (256 / (C / 8)) == 0, "chan_ln_gn: H*W must be a multiple of %d", 256 / (C / 8));
+  IDIFF_REQUIRE(aligned16(x) && aligned16(y) && aligned16(g), "chan_ln_gn: 16 B alignment");
+  GnFuse gf;
+  IDIFF_REQUIRE(gn_fuse_make(gf, fuse, B, C, G), "chan_ln_gn: incomplete gn_fuse description");
+  dim3 grid((unsigned)idiff_gn_stats_ntile(HW), (unsigned)B);
+  chan_ln_gn_kernel<<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, g, (__nv_bfloat16*)y, ln_eps, HW, C, gf);
+  return check_launch("chan_ln_gn");
+}
 
 int idiff_gn_stats(const void* src, float* partial, int B, int HW, int C, int G, void* stream) {
   IDIFF_REQUIRE(src && partial && B > 0 && HW > 0, "gn_stats: bad arguments");

@@ -10,6 +10,7 @@
 #include <cuda_bf16.h>
 
 #include <functional>
+#include <stdlib.h>
 #include <map>
 #include <memory>
 #include <string>
@@ -152,6 +153,7 @@ struct Net {
   std::map<std::string, Cross> cross;
   std::map<std::string, const float*> vec;                 // loose fp32 vectors (prenorm gains ...)
   std::map<std::string, int> ss_off;
+  bool fuse_gn = true;                                       // IDIFF_NO_GN_FUSE=1: partial rows + idiff_gn_finalize launches
   const void *stem_w = nullptr, *head_w = nullptr;
   float head_bias = 0.f;
   const float *w1t = nullptr, *b1 = nullptr, *w2t = nullptr, *b2 = nullptr, *wss = nullptr, *bss = nullptr;
@@ -175,6 +177,9 @@ struct Plan {
   std::vector<void*> owned;                                // cudaMalloc'd buffers
   std::map<std::string, void*> scratch;                    // shared temporaries by (name, bytes)
   std::vector<std::unique_ptr<idiff_gemm_params>> params;
+  std::vector<std::unique_ptr<idiff_gn_fuse>> fuses;        // GroupNorm finalize folded into the producing launch
+  void* gn_sums = nullptr;                                  // zeroed once; every fused launch leaves it zeroed again
+  unsigned int* gn_arrivals = nullptr;
   std::map<std::string, idiff_gemm_params*> ctx_slots;
   float *eps = nullptr, *temb = nullptr, *ss = nullptr;
   void* x_first = nullptr;
@@ -216,6 +221,7 @@ struct Plan {
     int k = 1, stride = 1, up = 0, a_silu = 0, epi = IDIFF_EPI_PLAIN, cin0 = -1, src0_ld = 0, NT = -1, out_ld = -1;
     const float *a_scale = nullptr, *a_shift = nullptr, *row_stats = nullptr, *res0_scale = nullptr, *res0_shift = nullptr, *ln_g = nullptr;
     float *gn_partial = nullptr, *out_stats = nullptr;
+    const idiff_gn_fuse* gn_fuse = nullptr;
     const void *res0 = nullptr, *res1 = nullptr, *w_override = nullptr;
     bool bias = true;
     const char* bias_img_slot = nullptr;
@@ -242,7 +248,8 @@ struct Plan {
     p->N = e.N;
     p->NT = o.NT < 0 ? e.NT : o.NT;
     p->a_silu = o.a_silu; p->epi = o.epi;
-    p->gn_groups = o.gn_partial ? 8 : 0;
+    p->gn_groups = (o.gn_partial || o.gn_fuse) ? 8 : 0;
+    p->gn_fuse = o.gn_fuse;
     p->out_ld = o.out_ld < 0 ? out.C : o.out_ld;
     p->src0 = src0.t; p->src1 = src1 ? src1->t : nullptr;
     p->a_scale = o.a_scale; p->a_shift = o.a_shift;
@@ -277,6 +284,33 @@ struct Plan {
     }
     ++n_launch;
   }
+  // idiff_gn_fuse for a producer launch (same role as unet.py::_Plan.gn_fuse_desc)
+  const idiff_gn_fuse* gn_fuse_desc(const Norm& nm, int C, int count, float eps_, int t_off, const char* tag, float** sc_out,
+                                    float** sh_out) {
+    if (!gn_sums) {
+      const size_t bytes = (size_t)B * IDIFF_GN_SLOTS * 32 * 2 * 8;
+      gn_sums = alloc(bytes);
+      gn_arrivals = (unsigned int*)alloc(16);
+      if (gn_sums && gn_arrivals && (cudaMemset(gn_sums, 0, bytes) != cudaSuccess || cudaMemset(gn_arrivals, 0, 16) != cudaSuccess)) err = 1;
+    }
+    float* sc = (float*)tmp(std::string(tag) + "_sc", (size_t)B * C * 4);
+    float* sh = (float*)tmp(std::string(tag) + "_sh", (size_t)B * C * 4);
+    fuses.emplace_back(new idiff_gn_fuse());
+    idiff_gn_fuse* f = fuses.back().get();
+    memset(f, 0, sizeof(*f));
+    f->sums = gn_sums; f->arrivals = gn_arrivals;
+    f->gamma = nm.g; f->beta = nm.b;
+    if (t_off >= 0) {
+      f->t_scale = ss + t_off;
+      f->t_shift = ss + t_off + C;
+      f->t_ld = shared_time ? 0 : net->S;
+    }
+    f->scale_out = sc; f->shift_out = sh;
+    f->count_per_group = count; f->eps = eps_;
+    *sc_out = sc;
+    *sh_out = sh;
+    return f;
+  }
   void gn_finalize(const float* partial, int ntile, const Norm& nm, int C, int G, int count, float eps_, int t_off,
                    const char* tag, float** sc_out, float** sh_out) {
     float* sc = (float*)tmp(std::string(tag) + "_sc", (size_t)B * C * 4);
@@ -298,18 +332,27 @@ struct Plan {
     const int h = src0.H, w = src0.W, cin = src0.C + (src1 ? src1->C : 0), count = h * w * (cout / 8);
     const Entry &c1 = net->conv.at(prefix + ".conv1"), &c2 = net->conv.at(prefix + ".conv2");
     Act y1 = act(h, w, cout, false, "y1"), y2 = act(h, w, cout, false, "y2");
-    const int nt1 = gn_rows(c1, src1, y1), nt2 = gn_rows(c2, nullptr, y2);
-    float* part1 = (float*)tmp("gnp1", (size_t)B * nt1 * 16 * 4);
-    float* part2 = (float*)tmp("gnp2", (size_t)B * nt2 * 16 * 4);
-    GemmOpt o1;
-    o1.k = 3; o1.gn_partial = part1;
-    gemm(src0, src1, c1, y1, o1);
     float *sc1, *sh1, *sc2, *sh2;
-    gn_finalize(part1, nt1, net->norm.at(prefix + ".norm1"), cout, 8, count, 1e-5f, net->ss_off.at(prefix), "gn1", &sc1, &sh1);
-    GemmOpt o2;
-    o2.k = 3; o2.a_scale = sc1; o2.a_shift = sh1; o2.a_silu = 1; o2.gn_partial = part2;
-    gemm(y1, nullptr, c2, y2, o2);
-    gn_finalize(part2, nt2, net->norm.at(prefix + ".norm2"), cout, 8, count, 1e-5f, -1, "gn2", &sc2, &sh2);
+    GemmOpt o1, o2;
+    o1.k = 3;
+    o2.k = 3; o2.a_silu = 1;
+    if (net->fuse_gn) {
+      o1.gn_fuse = gn_fuse_desc(net->norm.at(prefix + ".norm1"), cout, count, 1e-5f, net->ss_off.at(prefix), "gn1", &sc1, &sh1);
+      gemm(src0, src1, c1, y1, o1);
+      o2.a_scale = sc1; o2.a_shift = sh1;
+      o2.gn_fuse = gn_fuse_desc(net->norm.at(prefix + ".norm2"), cout, count, 1e-5f, -1, "gn2", &sc2, &sh2);
+      gemm(y1, nullptr, c2, y2, o2);
+    } else {
+      const int nt1 = gn_rows(c1, src1, y1), nt2 = gn_rows(c2, nullptr, y2);
+      float* part1 = (float*)tmp("gnp1", (size_t)B * nt1 * 16 * 4);
+      float* part2 = (float*)tmp("gnp2", (size_t)B * nt2 * 16 * 4);
+      o1.gn_partial = part1;
+      gemm(src0, src1, c1, y1, o1);
+      gn_finalize(part1, nt1, net->norm.at(prefix + ".norm1"), cout, 8, count, 1e-5f, net->ss_off.at(prefix), "gn1", &sc1, &sh1);
+      o2.a_scale = sc1; o2.a_shift = sh1; o2.gn_partial = part2;
+      gemm(y1, nullptr, c2, y2, o2);
+      gn_finalize(part2, nt2, net->norm.at(prefix + ".norm2"), cout, 8, count, 1e-5f, -1, "gn2", &sc2, &sh2);
+    }
     Act out = act(h, w, cout, want_stats);
     if (cin == cout) {
       const void *y = y2.t, *res = src0.t;
@@ -368,21 +411,30 @@ struct Plan {
     const std::string f = prefix + ".fn";
     const int Bv = B;
     Act y = act(h, w, C, false, "st_y");
-    {
+    float *sc, *sh;
+    if (net->fuse_gn && HW % (2048 / C) == 0) {              // channel LayerNorm + GroupNorm(32) statistics + finalize: one launch
+      const idiff_gn_fuse* fz = gn_fuse_desc(net->norm.at(f + ".norm"), C, HW * (C / 32), 1e-6f, -1, "gn32", &sc, &sh);
       const void* xin = x.t;
       const float* g = net->vec.at(prefix + ".prenorm");
       void* dst = y.t;
-      ops.push_back([=](void* s) { return idiff_chan_ln(xin, g, dst, 1e-5f, rows, C, s); });
+      ops.push_back([=](void* s) { return idiff_chan_ln_gn(xin, g, dst, 1e-5f, Bv, HW, C, 32, fz, s); });
+      ++n_launch;
+    } else {
+      {
+        const void* xin = x.t;
+        const float* g = net->vec.at(prefix + ".prenorm");
+        void* dst = y.t;
+        ops.push_back([=](void* s) { return idiff_chan_ln(xin, g, dst, 1e-5f, rows, C, s); });
+      }
+      const int ntile = idiff_gn_stats_ntile(HW);
+      float* part = (float*)tmp("st_gnp", (size_t)B * ntile * 32 * 2 * 4);
+      {
+        const void* src = y.t;
+        ops.push_back([=](void* s) { return idiff_gn_stats(src, part, Bv, HW, C, 32, s); });
+      }
+      n_launch += 2;
+      gn_finalize(part, ntile, net->norm.at(f + ".norm"), C, 32, HW * (C / 32), 1e-6f, -1, "gn32", &sc, &sh);
     }
-    const int ntile = idiff_gn_stats_ntile(HW);
-    float* part = (float*)tmp("st_gnp", (size_t)B * ntile * 32 * 2 * 4);
-    {
-      const void* src = y.t;
-      ops.push_back([=](void* s) { return idiff_gn_stats(src, part, Bv, HW, C, 32, s); });
-    }
-    n_launch += 2;
-    float *sc, *sh;
-    gn_finalize(part, ntile, net->norm.at(f + ".norm"), C, 32, HW * (C / 32), 1e-6f, -1, "gn32", &sc, &sh);
     Act h0 = act(h, w, C, true);
     GemmOpt o;
     o.k = 1; o.a_scale = sc; o.a_shift = sh; o.out_stats = h0.stats;
@@ -749,6 +801,10 @@ int idiff_unet_create(const idiff_unet_cfg* cfg, idiff_unet** out) {
   u->net.nf = cfg->nf;
   u->net.td = cfg->nf * 4;
   u->net.context_dim = cfg->context_dim;
+  {
+    const char* e = getenv("IDIFF_NO_GN_FUSE");               // A/B switch, same as unet.py
+    u->net.fuse_gn = !(e && e[0] == '1');
+  }
   u->net.dims.push_back(cfg->nf);
   for (int i = 0; i < cfg->n_levels; ++i) u->net.dims.push_back(cfg->nf * cfg->ch_mult[i]);
   *out = u;

@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import GemmParams, check
+from ._lib import GN_SLOTS, GemmParams, GnFuse, check
 
 _PTR_FIELDS = {"src0", "src1", "a_scale", "a_shift", "w", "bias", "bias_img", "row_stats", "wsum", "res0", "res1",
                "res0_scale", "res0_shift", "ln_g", "out", "gn_partial", "out_row_stats"}
@@ -128,6 +128,35 @@ def gn_finalize(partial, gamma, beta, count, eps, t_scale=None, t_shift=None, t_
                                        None if t_shift is None else t_shift.data_ptr(), t_ld, sc.data_ptr(),
                                        sh.data_ptr(), B, Cc, G, count, eps, _s(partial)), "gn_finalize")
     return sc, sh
+
+
+def make_gn_fuse(B, gamma, beta, count, eps, G=8, t_scale=None, t_shift=None, t_ld=0, state=None):
+    """``idiff_gn_fuse`` for a producer launch (GroupNorm finalize folded into the kernel).  Returns
+    ``(fuse, scale, shift, state)``; ``state = (sums, arrivals)`` is zeroed device memory that the kernel leaves zeroed
+    again, so one pair can be passed on from launch to launch."""
+    dev, Cc = gamma.device, gamma.numel()
+    if state is None:
+        state = (torch.zeros(B * GN_SLOTS * G * 2, dtype=torch.int64, device=dev), torch.zeros(4, dtype=torch.int32, device=dev))
+    sc = torch.full((B, Cc), float("nan"), dtype=torch.float32, device=dev)
+    sh = torch.full_like(sc, float("nan"))
+    f = GnFuse()
+    f.sums, f.arrivals = state[0].data_ptr(), state[1].data_ptr()
+    f.gamma, f.beta = gamma.data_ptr(), beta.data_ptr()
+    if t_scale is not None:
+        f.t_scale, f.t_shift, f.t_ld = t_scale.data_ptr(), t_shift.data_ptr(), t_ld
+    f.scale_out, f.shift_out = sc.data_ptr(), sh.data_ptr()
+    f.count_per_group, f.eps = count, eps
+    f._keepalive = [gamma, beta, t_scale, t_shift, sc, sh, state]
+    return f, sc, sh, state
+
+
+def chan_ln_gn(x, g, fuse: GnFuse, G=32, eps=1e-5):
+    """Channel LayerNorm (y returned) + GroupNorm(G) statistics of y + their finalize (rows of ``fuse``) in one launch."""
+    B, H, W, Cc = x.shape
+    y = torch.empty_like(x)
+    check(_lib.lib().idiff_chan_ln_gn(x.data_ptr(), g.data_ptr(), y.data_ptr(), eps, B, H * W, Cc, G, C.byref(fuse), _s(x)),
+          "chan_ln_gn")
+    return y
 
 
 def block_tail(y, scale, shift, res, want_stats=False, eps=1e-5):

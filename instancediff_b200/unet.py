@@ -21,7 +21,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import _lib
-from ._lib import EPI_GEGLU, EPI_LN_OUT, EPI_PLAIN, EPI_QSOFTMAX, GemmParams, check
+from ._lib import EPI_GEGLU, EPI_LN_OUT, EPI_PLAIN, EPI_QSOFTMAX, GN_SLOTS, GemmParams, GnFuse, check
 from .packing import (fold_layernorm, interleave_geglu, pack_conv3_rowpair, pack_conv_weight, pack_head_weight,
                       pack_stem_weight)
 
@@ -149,6 +149,8 @@ class ConditionalUNet:
         # them on the generic engine (A/B measurements)
         self.use_rowpair = os.environ.get("IDIFF_NO_ROWPAIR", "0") != "1"
         self.rowpair_packed_silu = os.environ.get("IDIFF_ROWPAIR_F32_SILU", "0") != "1"
+        # GroupNorm finalize folded into the producing conv (IDIFF_NO_GN_FUSE=1: partial rows + idiff_gn_finalize launches)
+        self.fuse_gn = os.environ.get("IDIFF_NO_GN_FUSE", "0") != "1"
         self.pk: Optional[Dict[str, dict]] = None    # packed weights: built lazily, ONCE per weight load
         self._version = 0
         self._init_params(seed)
@@ -477,6 +479,7 @@ class _Plan:
         self.ctx_slots: Dict[str, GemmParams] = {}
         self.named: Dict[str, _Act] = {}      # block outputs by module name (layer-wise parity tests)
         self.n_launch = 0
+        self._gn_sums = self._gn_arrivals = None
         self._build()
 
     # ---- buffers
@@ -500,7 +503,8 @@ class _Plan:
     def gemm(self, src0: _Act, src1: Optional[_Act], entry: dict, out: _Act, *, k=1, stride=1, up=0,
              a_scale=None, a_shift=None, a_silu=0, epi=EPI_PLAIN, gn_partial=None, bias=True, bias_img_slot=None,
              row_stats=None, res0=None, res1=None, res0_scale=None, res0_shift=None, ln_g=None, out_stats=None,
-             qscale=1.0, ln_eps=1e-5, cin0=None, src0_ld=0, w_override=None, w_image_stride=0, NT=None, out_ld=None):
+             qscale=1.0, ln_eps=1e-5, cin0=None, src0_ld=0, w_override=None, w_image_stride=0, NT=None, out_ld=None,
+             gn_fuse=None):
         p = GemmParams()
         p.B, p.H, p.W = self.B, out.H, out.W
         p.ksize, p.stride, p.up0 = k, stride, up
@@ -520,7 +524,9 @@ class _Plan:
                 p.NT = 128
                 w_override = self.net.packed_variant(entry["name"], 128)
         p.a_silu, p.epi = a_silu, epi
-        p.gn_groups = GN_GROUPS if gn_partial is not None else 0
+        p.gn_groups = GN_GROUPS if (gn_partial is not None or gn_fuse is not None) else 0
+        if gn_fuse is not None:                  # GroupNorm finalize folded into this launch (csrc/gn_fuse.cuh)
+            p.gn_fuse = C.pointer(gn_fuse)
         p.out_ld = out.C if out_ld is None else out_ld
         p.src0, p.src1 = _ptr(src0.t), _ptr(src1.t if src1 is not None else None)
         p.a_scale, p.a_shift = _ptr(a_scale), _ptr(a_shift)
@@ -585,6 +591,27 @@ class _Plan:
         """rows of GroupNorm partial sums per image written by idiff_conv_gemm (one per epilogue warp and tile)"""
         return self.L.idiff_conv_gemm_gn_rows(H, W)
 
+    def gn_fuse_desc(self, norm, Cc, G, count, eps, t_off=None, tag="gn"):
+        """idiff_gn_fuse for a producer launch: the kernel adds its GroupNorm sums as exact integers and its last CTA writes
+        the (scale, shift) rows the next layer applies on load -- no idiff_gn_finalize launch."""
+        B = self.B
+        if self._gn_sums is None:                # one zeroed pair serves every layer of the plan (stream-ordered, self-cleaning)
+            self._gn_sums = torch.zeros(B * GN_SLOTS * 32 * 2, dtype=torch.int64, device=self.dev)
+            self._gn_arrivals = torch.zeros(4, dtype=torch.int32, device=self.dev)
+        sc = self.tmp(tag + "_sc", (B, Cc), torch.float32)
+        sh = self.tmp(tag + "_sh", (B, Cc), torch.float32)
+        f = GnFuse()
+        f.sums, f.arrivals = self._gn_sums.data_ptr(), self._gn_arrivals.data_ptr()
+        f.gamma, f.beta = _ptr(norm["g"]), _ptr(norm["b"])
+        if t_off is not None:
+            f.t_scale = self.ss.data_ptr() + 4 * t_off
+            f.t_shift = self.ss.data_ptr() + 4 * (t_off + Cc)
+            f.t_ld = 0 if self.shared_time else self.net.S
+        f.scale_out, f.shift_out = _ptr(sc), _ptr(sh)
+        f.count_per_group, f.eps = count, eps
+        self.keep.append(f)
+        return f, sc, sh
+
     def gn_finalize(self, partial, ntile, norm, C, G, count, eps, t_off=None, tag="gn"):
         sc = self.tmp(tag + "_sc", (self.B, C), torch.float32)
         sh = self.tmp(tag + "_sh", (self.B, C), torch.float32)
@@ -609,15 +636,22 @@ class _Plan:
         count = H * W * (cout // GN_GROUPS)
         y1 = self.act(H, W, cout, tmp_name="y1")
         y2 = self.act(H, W, cout, tmp_name="y2")
-        nt1 = self.gn_rows(pk[prefix + ".conv1"], src0, src1, y1)
-        nt2 = self.gn_rows(pk[prefix + ".conv2"], y1, None, y2)
-        part1 = self.tmp("gnp1", (B, nt1, GN_GROUPS, 2), torch.float32)
-        part2 = self.tmp("gnp2", (B, nt2, GN_GROUPS, 2), torch.float32)
-        self.gemm(src0, src1, pk[prefix + ".conv1"], y1, k=3, gn_partial=part1)
-        sc1, sh1 = self.gn_finalize(part1, nt1, pk[prefix + ".norm1"], cout, GN_GROUPS, count, 1e-5,
-                                    t_off=self.net._ss_off[prefix], tag="gn1")
-        self.gemm(y1, None, pk[prefix + ".conv2"], y2, k=3, a_scale=sc1, a_shift=sh1, a_silu=1, gn_partial=part2)
-        sc2, sh2 = self.gn_finalize(part2, nt2, pk[prefix + ".norm2"], cout, GN_GROUPS, count, 1e-5, tag="gn2")
+        if self.net.fuse_gn:
+            f1, sc1, sh1 = self.gn_fuse_desc(pk[prefix + ".norm1"], cout, GN_GROUPS, count, 1e-5,
+                                             t_off=self.net._ss_off[prefix], tag="gn1")
+            self.gemm(src0, src1, pk[prefix + ".conv1"], y1, k=3, gn_fuse=f1)
+            f2, sc2, sh2 = self.gn_fuse_desc(pk[prefix + ".norm2"], cout, GN_GROUPS, count, 1e-5, tag="gn2")
+            self.gemm(y1, None, pk[prefix + ".conv2"], y2, k=3, a_scale=sc1, a_shift=sh1, a_silu=1, gn_fuse=f2)
+        else:
+            nt1 = self.gn_rows(pk[prefix + ".conv1"], src0, src1, y1)
+            nt2 = self.gn_rows(pk[prefix + ".conv2"], y1, None, y2)
+            part1 = self.tmp("gnp1", (B, nt1, GN_GROUPS, 2), torch.float32)
+            part2 = self.tmp("gnp2", (B, nt2, GN_GROUPS, 2), torch.float32)
+            self.gemm(src0, src1, pk[prefix + ".conv1"], y1, k=3, gn_partial=part1)
+            sc1, sh1 = self.gn_finalize(part1, nt1, pk[prefix + ".norm1"], cout, GN_GROUPS, count, 1e-5,
+                                        t_off=self.net._ss_off[prefix], tag="gn1")
+            self.gemm(y1, None, pk[prefix + ".conv2"], y2, k=3, a_scale=sc1, a_shift=sh1, a_silu=1, gn_partial=part2)
+            sc2, sh2 = self.gn_finalize(part2, nt2, pk[prefix + ".norm2"], cout, GN_GROUPS, count, 1e-5, tag="gn2")
         out = self.act(H, W, cout, stats=want_stats)
         if cin == cout:
             L = self.L
@@ -674,16 +708,24 @@ class _Plan:
         f = prefix + ".fn"
         rows, HW = B * H * W, H * W
         y = self.act(H, W, Cc, tmp_name="st_y")
-        a_ln = (_ptr(x.t), _ptr(pk[prefix + ".prenorm"]["g"]), _ptr(y.t), 1e-5, rows, Cc)
-        self.ops.append(lambda s: check(L.idiff_chan_ln(*a_ln, s), "chan_ln"))
-        self.op_info.append(("chan_ln", 0.0, f"C{Cc} @{H}x{W}"))
-        ntile = L.idiff_gn_stats_ntile(HW)
-        part = self.tmp("st_gnp", (B, ntile, 32, 2), torch.float32)
-        a_gs = (_ptr(y.t), _ptr(part), B, HW, Cc, 32)
-        self.ops.append(lambda s: check(L.idiff_gn_stats(*a_gs, s), "gn_stats"))
-        self.op_info.append(("gn_stats", 0.0, f"C{Cc} @{H}x{W}"))
-        self.n_launch += 2
-        sc, sh = self.gn_finalize(part, ntile, pk[f + ".norm"], Cc, 32, HW * (Cc // 32), 1e-6, tag="gn32")
+        if self.net.fuse_gn and HW % (2048 // Cc) == 0:
+            # channel LayerNorm + GroupNorm(32) statistics + finalize in one launch
+            fz, sc, sh = self.gn_fuse_desc(pk[f + ".norm"], Cc, 32, HW * (Cc // 32), 1e-6, tag="gn32")
+            a_lg = (_ptr(x.t), _ptr(pk[prefix + ".prenorm"]["g"]), _ptr(y.t), 1e-5, B, HW, Cc, 32, C.byref(fz))
+            self.ops.append(lambda s: check(L.idiff_chan_ln_gn(*a_lg, s), "chan_ln_gn"))
+            self.op_info.append(("chan_ln_gn", 0.0, f"C{Cc} @{H}x{W}"))
+            self.n_launch += 1
+        else:
+            a_ln = (_ptr(x.t), _ptr(pk[prefix + ".prenorm"]["g"]), _ptr(y.t), 1e-5, rows, Cc)
+            self.ops.append(lambda s: check(L.idiff_chan_ln(*a_ln, s), "chan_ln"))
+            self.op_info.append(("chan_ln", 0.0, f"C{Cc} @{H}x{W}"))
+            ntile = L.idiff_gn_stats_ntile(HW)
+            part = self.tmp("st_gnp", (B, ntile, 32, 2), torch.float32)
+            a_gs = (_ptr(y.t), _ptr(part), B, HW, Cc, 32)
+            self.ops.append(lambda s: check(L.idiff_gn_stats(*a_gs, s), "gn_stats"))
+            self.op_info.append(("gn_stats", 0.0, f"C{Cc} @{H}x{W}"))
+            self.n_launch += 2
+            sc, sh = self.gn_finalize(part, ntile, pk[f + ".norm"], Cc, 32, HW * (Cc // 32), 1e-6, tag="gn32")
         h0 = self.act(H, W, Cc, stats=True, tmp_name=None)
         self.gemm(y, None, pk[f + ".proj_in"], h0, k=1, a_scale=sc, a_shift=sh, a_silu=0, out_stats=h0.stats)
         qkv = self.act(H, W, 3 * Cc, tmp_name="st_qkv")

@@ -91,12 +91,12 @@ def test_conv_matches_fp32_reference(case):
     assert rel_err(out, ref) <= TOL, describe(out, ref, str(case))
 
 
-def _run_rowpair(B, H, W, affine, seed=0, gn=False, packed=False):
+def _run_rowpair(B, H, W, affine, seed=0, gn=False, packed=False, gn_fuse=None, src=None, gen=None):
     """idiff_conv3_rowpair (full-width MMA formulation of the 3x3 64 -> 64 layers) on the same contract."""
     from instancediff_b200 import _lib, ops
     from instancediff_b200.packing import pack_conv3_rowpair
-    g = torch.Generator().manual_seed(seed)
-    src0 = rand_act(B, H, W, 64, g)
+    g = torch.Generator().manual_seed(seed) if gen is None else gen
+    src0 = rand_act(B, H, W, 64, g) if src is None else src
     w = (torch.rand(64, 64, 3, 3, generator=g) * 2 - 1).cuda() / math.sqrt(64 * 9)
     bias = (torch.rand(64, generator=g) * 2 - 1).cuda() * 0.1
     sc = sh = None
@@ -108,7 +108,8 @@ def _run_rowpair(B, H, W, affine, seed=0, gn=False, packed=False):
     part = torch.full((B, rows, 8, 2), float("nan"), device="cuda") if gn else None
     p = ops.make_gemm_params(B=B, H=H, W=W, ksize=3, stride=1, cin0=64, N=64, NT=64, a_silu=int(affine) * (3 if packed else 1),
                              epi=0, out_ld=64, src0=src0, a_scale=sc, a_shift=sh, w=pack_conv3_rowpair(w.cpu()).cuda(), bias=bias,
-                             out=out, gn_groups=8 if gn else 0, gn_partial=part)
+                             out=out, gn_groups=8 if (gn or gn_fuse is not None) else 0, gn_partial=part,
+                             **({"gn_fuse": gn_fuse} if gn_fuse is not None else {}))
     assert _lib.lib().idiff_conv3_rowpair_supported(p)
     ops.conv3_rowpair(p)
     torch.cuda.synchronize()
@@ -225,6 +226,88 @@ def test_groupnorm_partials_with_a_split_n_tile(N, NT):
     assert not torch.isnan(part_b).any() and torch.equal(part_a, part_b)
     r = ref.reshape(B, H * W, 8, N // 8)
     assert torch.allclose(part_b.sum(dim=1)[..., 0], r.sum(dim=(1, 3)), rtol=1e-3, atol=1e-2)
+
+
+def _fuse_for(B, N, H, W, seed, with_time):
+    import ctypes
+    from instancediff_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    gamma, beta = (torch.rand(N, generator=g) + 0.5).cuda(), (torch.rand(N, generator=g) - 0.5).cuda()
+    ts = tb = None
+    if with_time:
+        ts, tb = (torch.rand(B, N, generator=g) - 0.5).cuda(), (torch.rand(B, N, generator=g) - 0.5).cuda()
+    f, sc, sh, state = ops.make_gn_fuse(B, gamma, beta, H * W * (N // 8), 1e-5, t_scale=ts, t_shift=tb, t_ld=N if with_time else 0)
+    return f, ctypes.pointer(f), sc, sh, state, gamma, beta, ts, tb
+
+
+@pytest.mark.parametrize("N,NT,H,W,with_time", [(64, 64, 32, 24, True), (128, 128, 32, 24, False), (256, 128, 16, 40, True),
+                                                (256, 256, 32, 32, False)])
+def test_groupnorm_finalize_folded_into_the_conv(N, NT, H, W, with_time):
+    """gn_fuse: exact integer sums + last-CTA finalize == partial rows + idiff_gn_finalize (up to fp32 rounding of the old
+    path's sums), equals torch's GroupNorm, and leaves its state zeroed for the next launch."""
+    from instancediff_b200 import _lib, ops
+    B = 3
+    f, fp, sc, sh, state, gamma, beta, ts, tb = _fuse_for(B, N, H, W, 21, with_time)
+    out, ref, _ = _run(B, H, W, 128, 0, N, 3, seed=4, NT=NT, gn_groups=8, gn_fuse=fp)
+    rows = _lib.lib().idiff_conv_gemm_gn_rows(H, W)
+    part = torch.zeros(B, rows, 8, 2, device="cuda")
+    out2, _, _ = _run(B, H, W, 128, 0, N, 3, seed=4, NT=NT, gn_groups=8, gn_partial=part)
+    sc2, sh2 = ops.gn_finalize(part, gamma, beta, H * W * (N // 8), 1e-5, t_scale=ts, t_shift=tb, t_ld=N if with_time else 0)
+    assert torch.equal(out, out2)
+    assert not torch.isnan(sc).any() and not torch.isnan(sh).any(), "affine rows not written"
+    assert torch.allclose(sc, sc2, rtol=2e-5, atol=1e-6) and torch.allclose(sh, sh2, rtol=2e-5, atol=2e-6), \
+        ((sc - sc2).abs().max(), (sh - sh2).abs().max())
+    assert int(state[0].abs().max()) == 0 and int(state[1][0]) == 0, "gn_fuse state not left zeroed"
+    gn = F.group_norm(ref.permute(0, 3, 1, 2), 8, gamma, beta, 1e-5).permute(0, 2, 3, 1)
+    if with_time:
+        gn = gn * (1 + ts[:, None, None, :]) + tb[:, None, None, :]
+    y = ref * sc[:, None, None, :] + sh[:, None, None, :]
+    assert rel_err(y, gn) <= 1e-3, describe(y, gn, "gn fused")
+    # second launch on the same state (what a plan does layer after layer), and a batch shard: rows are per image
+    sc_first = sc.clone()
+    out3, _, _ = _run(B, H, W, 128, 0, N, 3, seed=4, NT=NT, gn_groups=8, gn_fuse=fp)
+    assert torch.equal(sc, sc_first) and int(state[0].abs().max()) == 0
+
+
+def test_groupnorm_finalize_folded_is_invariant_to_the_batch_shard():
+    """exact integer sums: an image's affine rows do not depend on the batch it is processed in (sharding invariance)"""
+    from instancediff_b200 import ops
+    import ctypes
+    N, H, W = 64, 32, 128
+    g = torch.Generator().manual_seed(2)
+    gamma, beta = (torch.rand(N, generator=g) + 0.5).cuda(), (torch.rand(N, generator=g) - 0.5).cuda()
+    res = {}
+    src4 = rand_act(4, H, W, 64, g)
+    w_state = g.get_state()
+    for B in (4, 2):
+        g.set_state(w_state)                                  # same weights and bias for both batch sizes
+        f, sc, sh, _ = ops.make_gn_fuse(B, gamma, beta, H * W * 8, 1e-5)
+        _, ref, _ = _run_rowpair(B, H, W, False, gn_fuse=ctypes.pointer(f), src=src4[:B].contiguous(), gen=g)
+        res[B] = (sc.clone(), sh.clone(), ref)
+        assert not torch.isnan(sc).any()
+    assert torch.equal(res[4][0][:2], res[2][0]) and torch.equal(res[4][1][:2], res[2][1])
+    gn = F.group_norm(res[2][2].permute(0, 3, 1, 2), 8, gamma, beta, 1e-5).permute(0, 2, 3, 1)
+    y = res[2][2] * res[2][0][:, None, None, :] + res[2][1][:, None, None, :]
+    assert rel_err(y, gn) <= 1e-3
+
+
+def test_chan_ln_gn_equals_the_three_launch_chain():
+    """idiff_chan_ln_gn == idiff_chan_ln -> idiff_gn_stats -> idiff_gn_finalize (SpatialTransformer entry)"""
+    from instancediff_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    B, H, W, Cc = 3, 32, 32, 256
+    x = rand_act(B, H, W, Cc, g)
+    gain = (torch.rand(Cc, generator=g) + 0.5).cuda()
+    gamma, beta = (torch.rand(Cc, generator=g) + 0.5).cuda(), (torch.rand(Cc, generator=g) - 0.5).cuda()
+    f, sc, sh, state = ops.make_gn_fuse(B, gamma, beta, H * W * (Cc // 32), 1e-6, G=32)
+    y = ops.chan_ln_gn(x, gain, f, 32)
+    y_ref = ops.chan_ln(x, gain)
+    part = ops.gn_stats(y_ref, 32)
+    sc2, sh2 = ops.gn_finalize(part, gamma, beta, H * W * (Cc // 32), 1e-6)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref)
+    assert torch.allclose(sc, sc2, rtol=2e-5, atol=1e-6) and torch.allclose(sh, sh2, rtol=2e-5, atol=2e-6)
+    assert int(state[0].abs().max()) == 0 and int(state[1][0]) == 0
 
 
 def test_layernorm_fold_and_row_stats():
