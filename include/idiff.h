@@ -275,7 +275,7 @@ int idiff_chan_ln(const void* x, const float* g, void* y, float eps, size_t rows
 
 /* idiff_chan_ln + idiff_gn_stats + idiff_gn_finalize in one launch (entry of the SpatialTransformer): y = ChanLN(x)*g
  * in bf16, GroupNorm(G groups) statistics of the rounded y accumulated as exact integers, affine written by the last
- * CTA (see idiff_gn_fuse).  H*W must be a multiple of 2048 / C. */
+ * CTA (see idiff_gn_fuse).  H*W must be a multiple of 32. */
 int idiff_chan_ln_gn(const void* x, const float* g, void* y, float ln_eps, int B, int HW, int C, int G,
                      const idiff_gn_fuse* fuse, void* stream);
 

@@ -187,36 +187,42 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ parti
 
 // ---- channel LayerNorm + GroupNorm statistics + GroupNorm finalize in ONE launch (SpatialTransformer entry) ------
 // y = ChanLN(x) * gain (bf16, what idiff_chan_ln writes); the GroupNorm sums are taken over the ROUNDED y (what
-// idiff_gn_stats would read back) and finished by the last CTA (gn_fuse.cuh).  grid = (ntile, B), block = 256.
+// idiff_gn_stats would read back) and finished by the last CTA (gn_fuse.cuh).  grid = (HW / CLG_ROWS, B), block = 256:
+// small tiles (32 rows: 1024 CTAs at 32 x 32, B = 32) and all of a thread's rows loaded before the first shuffle --
+// with 128-row tiles the kernel was a chain of 16 dependent load -> reduce rounds per thread on 14 warps per SM.
+constexpr int CLG_ROWS = 32;
+template <int LPR>                                           // lanes per row = C / 8
 __global__ void __launch_bounds__(256)
 chan_ln_gn_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gain, __nv_bfloat16* __restrict__ y,
-                  float ln_eps, int HW, int C, const GnFuse gf) {
+                  float ln_eps, int HW, const GnFuse gf) {
+  constexpr int C = LPR * 8, RPS = 256 / LPR, NR = CLG_ROWS / RPS;   // rows per sweep, rows per thread (4 / 2 / 1)
   __shared__ float red[256][2];
   __shared__ float2 stat[1024];
   __shared__ int flag;
   const int b = blockIdx.y, tile = blockIdx.x;
-  const int lpr = C >> 3, rows_per_sweep = 256 / lpr;
-  const int c8 = threadIdx.x % lpr, roff = threadIdx.x / lpr;
-  const int r_end = min(HW, (tile + 1) * GN_TILE_ROWS);
+  const int c8 = threadIdx.x % LPR, roff = threadIdx.x / LPR;
   const float4 g0 = __ldg(reinterpret_cast<const float4*>(gain + c8 * 8));
   const float4 g1 = __ldg(reinterpret_cast<const float4*>(gain + c8 * 8 + 4));
   const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const size_t off0 = ((size_t)b * HW + (size_t)tile * CLG_ROWS + roff) * C + c8 * 8;
+  uint4 q[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) q[i] = __ldg(reinterpret_cast<const uint4*>(x + off0 + (size_t)i * RPS * C));
   float a1 = 0.f, a2 = 0.f;
-  // HW % rows_per_sweep == 0 is required by the launcher: the lanes of a row stay converged for the shuffles
-  for (int r = tile * GN_TILE_ROWS + roff; r < r_end; r += rows_per_sweep) {
-    const size_t off = ((size_t)b * HW + r) * C + c8 * 8;
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
     float f[8];
-    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(x + off)), f);
+    unpack_bf16x8(q[i], f);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s1 += f[e]; s2 += f[e] * f[e]; }
-    row_reduce(s1, s2, lpr);
+    row_reduce(s1, s2, LPR);
     const float mean = s1 / C, var = fmaxf(s2 / C - mean * mean, 0.f), rstd = rsqrtf(var + ln_eps);
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] = (f[e] - mean) * rstd * gg[e];
-    const uint4 q = pack_bf16x8(f);
-    *reinterpret_cast<uint4*>(y + off) = q;
-    unpack_bf16x8(q, f);
+    const uint4 o = pack_bf16x8(f);
+    *reinterpret_cast<uint4*>(y + off0 + (size_t)i * RPS * C) = o;
+    unpack_bf16x8(o, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) { a1 += f[e]; a2 += f[e] * f[e]; }
   }
@@ -227,8 +233,8 @@ chan_ln_gn_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__
   if (threadIdx.x < 2 * gf.G) {
     const int g = threadIdx.x >> 1, st = threadIdx.x & 1;
     float t = 0.f;
-    for (int ro = 0; ro < rows_per_sweep; ++ro)
-      for (int v = 0; v < vpg; ++v) t += red[ro * lpr + g * vpg + v][st];
+    for (int ro = 0; ro < RPS; ++ro)
+      for (int v = 0; v < vpg; ++v) t += red[ro * LPR + g * vpg + v][st];
     gn_fuse_add(gf, b, tile, g * 2 + st, t);
   }
   gn_fuse_finish<256>(gf, stat, &flag, threadIdx.x, 1, 1024);
@@ -449,12 +455,16 @@ int idiff_chan_ln_gn(const void* x, const float* g, void* y, float ln_eps, int B
   IDIFF_REQUIRE(x && g && y && fuse && B > 0 && HW > 0, "chan_ln_gn: bad arguments");
   if (int rc = check_c(C, "chan_ln_gn")) return rc;
   IDIFF_REQUIRE(G > 0 && G <= 128 && C % G == 0 && (C / G) % 8 == 0, "chan_ln_gn: unsupported groups %d", G);
-  IDIFF_REQUIRE(HW % (256 / (C / 8)) == 0, "chan_ln_gn: H*W must be a multiple of %d", 256 / (C / 8));
+  IDIFF_REQUIRE(HW % CLG_ROWS == 0, "chan_ln_gn: H*W must be a multiple of %d", CLG_ROWS);
   IDIFF_REQUIRE(aligned16(x) && aligned16(y) && aligned16(g), "chan_ln_gn: 16 B alignment");
   GnFuse gf;
   IDIFF_REQUIRE(gn_fuse_make(gf, fuse, B, C, G), "chan_ln_gn: incomplete gn_fuse description");
-  dim3 grid((unsigned)idiff_gn_stats_ntile(HW), (unsigned)B);
-  chan_ln_gn_kernel<<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, g, (__nv_bfloat16*)y, ln_eps, HW, C, gf);
+  const dim3 grid((unsigned)(HW / CLG_ROWS), (unsigned)B);
+  const __nv_bfloat16* xp = (const __nv_bfloat16*)x;
+  __nv_bfloat16* yp = (__nv_bfloat16*)y;
+  if (C == 64) chan_ln_gn_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(xp, g, yp, ln_eps, HW, gf);
+  else if (C == 128) chan_ln_gn_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(xp, g, yp, ln_eps, HW, gf);
+  else chan_ln_gn_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(xp, g, yp, ln_eps, HW, gf);
   return check_launch("chan_ln_gn");
 }
 

@@ -153,7 +153,8 @@ struct Net {
   std::map<std::string, Cross> cross;
   std::map<std::string, const float*> vec;                 // loose fp32 vectors (prenorm gains ...)
   std::map<std::string, int> ss_off;
-  bool fuse_gn = true;                                       // IDIFF_NO_GN_FUSE=1: partial rows + idiff_gn_finalize launches
+  bool fuse_gn = false;                                      // IDIFF_GN_FUSE=1: finalize folded into the producing conv (see unet.py)
+  bool fuse_gn_st = true;                                    // IDIFF_NO_GN_FUSE_ST=1: chan_ln + gn_stats + gn_finalize launches
   const void *stem_w = nullptr, *head_w = nullptr;
   float head_bias = 0.f;
   const float *w1t = nullptr, *b1 = nullptr, *w2t = nullptr, *b2 = nullptr, *wss = nullptr, *bss = nullptr;
@@ -412,7 +413,7 @@ struct Plan {
     const int Bv = B;
     Act y = act(h, w, C, false, "st_y");
     float *sc, *sh;
-    if (net->fuse_gn && HW % (2048 / C) == 0) {              // channel LayerNorm + GroupNorm(32) statistics + finalize: one launch
+    if (net->fuse_gn_st && HW % 32 == 0) {              // channel LayerNorm + GroupNorm(32) statistics + finalize: one launch
       const idiff_gn_fuse* fz = gn_fuse_desc(net->norm.at(f + ".norm"), C, HW * (C / 32), 1e-6f, -1, "gn32", &sc, &sh);
       const void* xin = x.t;
       const float* g = net->vec.at(prefix + ".prenorm");
@@ -802,8 +803,10 @@ int idiff_unet_create(const idiff_unet_cfg* cfg, idiff_unet** out) {
   u->net.td = cfg->nf * 4;
   u->net.context_dim = cfg->context_dim;
   {
-    const char* e = getenv("IDIFF_NO_GN_FUSE");               // A/B switch, same as unet.py
-    u->net.fuse_gn = !(e && e[0] == '1');
+    const char* e = getenv("IDIFF_GN_FUSE");                  // A/B switches, same as unet.py
+    u->net.fuse_gn = e && e[0] == '1';
+    e = getenv("IDIFF_NO_GN_FUSE_ST");
+    u->net.fuse_gn_st = !(e && e[0] == '1');
   }
   u->net.dims.push_back(cfg->nf);
   for (int i = 0; i < cfg->n_levels; ++i) u->net.dims.push_back(cfg->nf * cfg->ch_mult[i]);

@@ -149,8 +149,13 @@ class ConditionalUNet:
         # them on the generic engine (A/B measurements)
         self.use_rowpair = os.environ.get("IDIFF_NO_ROWPAIR", "0") != "1"
         self.rowpair_packed_silu = os.environ.get("IDIFF_ROWPAIR_F32_SILU", "0") != "1"
-        # GroupNorm finalize folded into the producing conv (IDIFF_NO_GN_FUSE=1: partial rows + idiff_gn_finalize launches)
-        self.fuse_gn = os.environ.get("IDIFF_NO_GN_FUSE", "0") != "1"
+        # IDIFF_GN_FUSE=1: GroupNorm finalize folded into the producing conv (exact integer sums + last-CTA finalize, 44
+        # launches fewer per step).  Off by default: measured neutral to 0.8 % slower inside the captured step -- the
+        # finishing CTA's tail (fence, arrival, L2 round trip: ~2.5 us) costs what a dependent 2 us launch costs in a graph
+        # (profiles/README.md); the default keeps partial rows + idiff_gn_finalize.
+        self.fuse_gn = os.environ.get("IDIFF_GN_FUSE", "0") == "1"
+        # same for the SpatialTransformer entry (channel LayerNorm + GroupNorm(32) statistics + finalize in one launch)
+        self.fuse_gn_st = os.environ.get("IDIFF_NO_GN_FUSE_ST", "0") != "1"
         self.pk: Optional[Dict[str, dict]] = None    # packed weights: built lazily, ONCE per weight load
         self._version = 0
         self._init_params(seed)
@@ -708,7 +713,7 @@ class _Plan:
         f = prefix + ".fn"
         rows, HW = B * H * W, H * W
         y = self.act(H, W, Cc, tmp_name="st_y")
-        if self.net.fuse_gn and HW % (2048 // Cc) == 0:
+        if self.net.fuse_gn_st and HW % 32 == 0:
             # channel LayerNorm + GroupNorm(32) statistics + finalize in one launch
             fz, sc, sh = self.gn_fuse_desc(pk[f + ".norm"], Cc, 32, HW * (Cc // 32), 1e-6, tag="gn32")
             a_lg = (_ptr(x.t), _ptr(pk[prefix + ".prenorm"]["g"]), _ptr(y.t), 1e-5, B, HW, Cc, 32, C.byref(fz))

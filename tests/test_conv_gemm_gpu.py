@@ -291,19 +291,21 @@ def test_groupnorm_finalize_folded_is_invariant_to_the_batch_shard():
     assert rel_err(y, gn) <= 1e-3
 
 
-def test_chan_ln_gn_equals_the_three_launch_chain():
-    """idiff_chan_ln_gn == idiff_chan_ln -> idiff_gn_stats -> idiff_gn_finalize (SpatialTransformer entry)"""
+@pytest.mark.parametrize("B,H,W,Cc", [(3, 32, 32, 256), (40, 8, 8, 256), (2, 16, 16, 64), (2, 16, 24, 128)])
+def test_chan_ln_gn_equals_the_three_launch_chain(B, H, W, Cc):
+    """idiff_chan_ln_gn == idiff_chan_ln -> idiff_gn_stats -> idiff_gn_finalize (SpatialTransformer entry); B = 40 has more
+    (image, group) pairs than one pass of the finishing CTA's scratch holds"""
     from instancediff_b200 import ops
     g = torch.Generator().manual_seed(8)
-    B, H, W, Cc = 3, 32, 32, 256
+    G = min(32, Cc // 8)                                      # groups of at least 8 channels
     x = rand_act(B, H, W, Cc, g)
     gain = (torch.rand(Cc, generator=g) + 0.5).cuda()
     gamma, beta = (torch.rand(Cc, generator=g) + 0.5).cuda(), (torch.rand(Cc, generator=g) - 0.5).cuda()
-    f, sc, sh, state = ops.make_gn_fuse(B, gamma, beta, H * W * (Cc // 32), 1e-6, G=32)
-    y = ops.chan_ln_gn(x, gain, f, 32)
+    f, sc, sh, state = ops.make_gn_fuse(B, gamma, beta, H * W * (Cc // G), 1e-6, G=G)
+    y = ops.chan_ln_gn(x, gain, f, G)
     y_ref = ops.chan_ln(x, gain)
-    part = ops.gn_stats(y_ref, 32)
-    sc2, sh2 = ops.gn_finalize(part, gamma, beta, H * W * (Cc // 32), 1e-6)
+    part = ops.gn_stats(y_ref, G)
+    sc2, sh2 = ops.gn_finalize(part, gamma, beta, H * W * (Cc // G), 1e-6)
     torch.cuda.synchronize()
     assert torch.equal(y, y_ref)
     assert torch.allclose(sc, sc2, rtol=2e-5, atol=1e-6) and torch.allclose(sh, sh2, rtol=2e-5, atol=2e-6)

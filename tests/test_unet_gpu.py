@@ -107,6 +107,25 @@ def test_forward_layerwise_and_output(nets, shape, t):
     assert first_bad is None and e_out <= EPS_TOL, "\n".join(report + [describe(out, ref, "eps")])
 
 
+def test_groupnorm_finalize_variants_agree(nets):
+    """The three GroupNorm plumbing variants of the plan -- partial rows + idiff_gn_finalize (default), finalize folded
+    into the producing conv (fuse_gn, exact integer sums), separate chan_ln / gn_stats launches at the SpatialTransformer
+    entry (fuse_gn_st off) -- compute the same statistics up to fp32 summation order."""
+    from instancediff_b200 import ConditionalUNet
+    oracle, net = nets
+    x, mu, ctx = _inputs(2, 64, 64, seed=5)
+    ref = net(x, mu, 41.0, image_context=ctx).clone()
+    for kw in (dict(fuse_gn=True), dict(fuse_gn_st=False), dict(fuse_gn=True, fuse_gn_st=False)):
+        alt = ConditionalUNet(device="cuda")
+        alt.load_state_dict(oracle.state_dict())
+        for k, v in kw.items():
+            setattr(alt, k, v)
+        out = alt(x, mu, 41.0, image_context=ctx)
+        again = alt(x, mu, 41.0, image_context=ctx).clone()       # second pass on the self-cleaning sums
+        assert torch.equal(out, again), kw
+        assert rel_err(out, ref) <= 2e-3, (kw, describe(out, ref, "gn variants"))
+
+
 def test_time_tensor_and_wrapper_convention(nets):
     oracle, net = nets
     x, mu, ctx = _inputs(2, 32, 32, seed=5)
