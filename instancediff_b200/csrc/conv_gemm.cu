@@ -158,6 +158,23 @@ int make_map_box(CUtensorMap* tm, const void* base, int cols, int ld, int B, int
   return IDIFF_OK;
 }
 
+// 2-D view [rows][cols] of a bf16 matrix with row pitch ld (elements), box = box_c columns x box_r rows, no swizzle:
+// a {8, 128} box lands as 128 rows x 16 B = one 8-channel plane of the UMMA no-swizzle K-major layout
+// (linattn_fused.cu loads its raw activation tiles this way).
+int make_map_2d(CUtensorMap* tm, const void* base, int cols, long long rows, int ld, int box_c, int box_r) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(IDIFF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_r};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(IDIFF_ERR_CUDA, "cuTensorMapEncodeTiled (2-D) failed (%d)", (int)r);
+  return IDIFF_OK;
+}
+
 static unsigned long long* g_prof_dev = nullptr;
 unsigned long long* prof_buffer() {                 // shared with conv3_rowpair.cu (profiling builds)
   if (!g_prof_dev && cudaMalloc(&g_prof_dev, 16 * sizeof(unsigned long long)) != cudaSuccess) g_prof_dev = nullptr;

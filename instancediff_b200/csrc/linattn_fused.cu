@@ -18,10 +18,15 @@
 // x^ = (x - mean) * rstd is formed by the tile loader from the producer's per-pixel LayerNorm statistics (the gain
 // is folded into the weights), so all three passes see bit-identical operands (exp(k - max) <= 1 exactly).
 // Serves `self.model(x, self.mu, t*scale, **kwargs)`, utils/sde_utils.py:198.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_common.h"
 
 namespace idiff {
+
+int make_map_2d(CUtensorMap* tm, const void* base, int cols, long long rows, int ld, int box_c, int box_r);   // conv_gemm.cu
 
 constexpr int LF_PX = 128;                      // pixels per tile
 constexpr int LF_XP = LF_PX * 16 + 16;          // x^ plane pitch: odd multiple of 16 B -> conflict-free loader stores
@@ -489,16 +494,509 @@ la_out_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ st
   }
 }
 
+// =====================================================================================================
+// pass 2, version 2: the same arithmetic, ONE CTA per SM with its roles pipelined through mbarrier rings.
+//   warp 16     : TMA producer -- the RAW activation tile (bulk-tensor boxes of 8 channels x 128 pixels land as the
+//                 planes of the UMMA no-swizzle K-major layout), ring of 3 (C = 64) / 2 (C = 128) stages; Wq and
+//                 Weff[b] once per CTA by bulk copies
+//   warp 17     : MMA issuer: q = x Wq^T of tile i (accumulator i & 1), then out = Q Weff^T of tile i - 2
+//   warps 8-15  : two softmax groups, tiles of parity g: LayerNorm fold  u = acc - mean * wsum  (the MMA sees the raw
+//                 x; wsum = row sums of the bf16 Wq image, computed once per CTA), per-head softmax with the rstd
+//                 folded into the exponent, Q tile g -> shared memory
+//   warps 0-7   : two LayerNorm groups, tiles of parity g: channel LayerNorm + gain + residual + store
+// Version 1 ran 2 CTAs x (4 + 4) warps per SM, and in each CTA the chain store x^ -> q GEMM -> softmax -> out GEMM was
+// serial for the front group (the SM issued 2.1 instructions per clock of 4).  Here every role has two tiles in
+// flight and nobody normalises x on CUDA cores (v1: 22 instructions per 8 channels) -- the fold costs one FMA per q
+// value.  Numerics: x enters the tensor core unnormalised (one bf16 rounding less than x^), the fold is exact in
+// fp32 up to the cancellation acc - mean * wsum (harmless while |mean| / std of a pixel's channels is far below 2^12).
+// =====================================================================================================
+constexpr int LO2_THREADS = 640;
+template <int C>
+struct Out2Smem {
+  // Softmax is the long role (4 x (TMEM load + 32 exponentials + a shared-memory store) per pixel: ~5300 cycles per tile
+  // and group against ~1500 for the single-pass LayerNorm epilogue of C = 64), so C = 64 runs THREE softmax groups and ONE
+  // LayerNorm group; C = 128 (two-pass LayerNorm, 2 x 128 accumulator columns per tile) keeps two and two.
+  static constexpr int NSM = C == 64 ? 3 : 2, NLN = C == 64 ? 1 : 2;
+  static constexpr int NXS = C == 64 ? 6 : 2;                  // raw-tile stages; C = 64: a stage lives until the LayerNorm group has
+                                                               // read the residual from it (q GEMM of tile i + 3 .. LayerNorm of tile i)
+  static constexpr int XSTAGE = (C / 8) * LF_WP;               // [C/8 planes][128 pixels][8 channels]
+  static constexpr int X = 0, WQ = X + NXS * XSTAGE, WE = WQ + (C / 8) * LF_WP, Q = WE + 16 * C * 16,
+                       PAR = Q + NSM * 16 * LF_TP, BAR = PAR + (2 * C + 128) * 4, TOTAL = BAR + 256;
+};
+
+IDIFF_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(LO2_THREADS, 1)
+la_out2_kernel(const __grid_constant__ CUtensorMap tm_x, const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats,
+               const void* __restrict__ wq, const __nv_bfloat16* __restrict__ weff, const float* __restrict__ bias,
+               const float* __restrict__ gain, __nv_bfloat16* __restrict__ out, int HW, int tiles_per_cta, float qscale, float eps,
+               unsigned long long* prof_buf) {
+  using S = Out2Smem<C>;
+  constexpr bool kOnePass = C == 64;                             // LayerNorm epilogue keeps the whole row in registers
+  constexpr bool kResSmem = C == 64;                             // ... and reads the residual x back from the tile's shared-memory stage
+#ifdef IDIFF_PROF
+  // role counters of CTA (0, 0) (profiling builds, IDIFF_LA_PROF=1): 0 kernel  1 tiles  2 sm:wait q_full  3 sm:wait s_empty
+  // 4 sm:work  5 ln:wait o_full  6 ln:work  7 mma:wait x_full  8 mma:wait q_empty  9 mma:wait s_full  10 mma:wait o_empty
+  // 11 mma:issue  12 tma:wait x_empty  13 prologue  14 mma:wait weights
+  const bool prof = prof_buf != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  long long pc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define LP_T() (prof ? clock64() : 0ll)
+#define LP_ADD(i, t0) do { if (prof) pc[i] += clock64() - (t0); } while (0)
+#else
+  constexpr bool prof = false;
+#define LP_T() 0ll
+#define LP_ADD(i, t0) do { (void)(t0); } while (0)
+#endif
+  const long long t_kernel = LP_T();
+  extern __shared__ __align__(128) uint8_t sm[];
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(sm + S::BAR);  // [6] raw tile landed
+  uint64_t* x_empty = x_full + 6;                                // [6] q GEMM (and, C = 64, the LayerNorm group) has read the tile
+  uint64_t* q_full = x_empty + 6;                                // [3] q accumulator complete
+  uint64_t* q_empty = q_full + 3;                                // [3] softmax group has read it
+  uint64_t* s_full = q_empty + 3;                                // [3] Q tile written
+  uint64_t* s_empty = s_full + 3;                                // [3] out GEMM has read the Q tile
+  uint64_t* o_full = s_empty + 3;                                // [2] out accumulator complete
+  uint64_t* o_empty = o_full + 2;                                // [2] LayerNorm group has read it
+  uint64_t* w_bar = o_empty + 2;                                 // Wq and Weff[b] landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* par = reinterpret_cast<float*>(sm + S::PAR);           // [bias C | gain C | wsum 128]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int r_begin = blockIdx.x * tiles_per_cta * LF_PX;
+  const int ntiles = min(tiles_per_cta, (HW - r_begin) / LF_PX);
+  if (tid == 0) {
+    for (int i = 0; i < 6; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], kResSmem ? 5 : 1); }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 4);
+      mbar_init(&s_full[i], 4); mbar_init(&s_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4); }
+    mbar_init(w_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 17) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < C; i += LO2_THREADS) {
+    par[i] = __ldg(bias + i);
+    par[C + i] = __ldg(gain + i);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  LP_ADD(13, t_kernel);
+  // registers per warpgroup (set at the top of each role branch), same budget as the conv engine:
+  // 256 * 112 + 256 * 104 + 128 * 40 <= 640 * 96
+  const __nv_bfloat16* xb = x + (size_t)b * HW * C;
+  const float2* sb = stats + (size_t)b * HW;
+  __nv_bfloat16* ob = out + (size_t)b * HW * C;
+  const int quarter = warp & 3, px = quarter * 32 + lane;
+  const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+  constexpr int NSM = S::NSM, NLN = S::NLN, kSmWarp0 = 4 * NLN;
+  constexpr uint32_t kOutCol = NSM * 128;                        // two out accumulators behind the NSM q accumulators
+
+  if (warp >= 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  if (warp == 16) {
+    // ------------------------------------------------ TMA producer ------------------------------------------
+    const bool leader = elect_one();
+    constexpr uint32_t wq_bytes = (C / 8) * LF_WP, we_bytes = 16 * C * 16;
+    if (leader) {
+      mbar_arrive_expect_tx(w_bar, wq_bytes + we_bytes);
+      bulk_g2s(sm + S::WQ, wq, wq_bytes, w_bar);
+      bulk_g2s(sm + S::WE, weff + (size_t)b * C * 128, we_bytes, w_bar);
+    }
+    for (int i = 0; i < ntiles; ++i) {
+      const int s = i % S::NXS;
+      long long tp = LP_T();
+      if (i >= S::NXS) mbar_wait(&x_empty[s], (uint32_t)(((i / S::NXS) - 1) & 1), 411);
+      LP_ADD(12, tp);
+      if (leader) {
+        mbar_arrive_expect_tx(&x_full[s], (uint32_t)S::XSTAGE);
+        const int row = b * HW + r_begin + i * LF_PX;
+#pragma unroll 1
+        for (int pl = 0; pl < C / 8; ++pl) tma_load_2d(sm + S::X + s * S::XSTAGE + pl * LF_WP, &tm_x, pl * 8, row, &x_full[s]);
+      }
+      __syncwarp();
+    }
+#ifdef IDIFF_PROF
+    if (prof && lane == 0) prof_buf[12] = pc[12];
+#endif
+  } else if (warp == 17) {
+    // ------------------------------------------------ MMA issuer --------------------------------------------
+    const bool leader = elect_one();
+    const uint32_t smem0 = smem_u32(sm);
+    const uint32_t idesc1 = umma_idesc_bf16(128, 128, 0), idesc3 = umma_idesc_bf16(128, C, 0);
+    const uint32_t x_lo = umma_desc_lo(smem0 + S::X, LF_WP), wq_lo = umma_desc_lo(smem0 + S::WQ, LF_WP);
+    const uint32_t q_lo = umma_desc_lo(smem0 + S::Q, LF_TP), we_lo = umma_desc_lo(smem0 + S::WE, C * 16);
+    const uint32_t k_hi = umma_desc_hi(128);
+    long long tp = LP_T();
+    mbar_wait(w_bar, 0, 412);
+    LP_ADD(14, tp);
+    tc_fence_after();
+    // The out GEMM trails the q GEMM by NSM tiles in this loop: the q accumulator of tile i is free as soon as its
+    // softmax group has read tile i - NSM (one head before that group finishes), so issuing the q GEMM of tile i BEFORE
+    // waiting for the Q tile of i - NSM has the next accumulator ready when the group comes back for it (with a lag of
+    // one tile every softmax group idled for a whole q GEMM per tile: 760 of 4050 cycles).
+    for (int i = 0; i < ntiles + NSM; ++i) {
+      if (i < ntiles) {                                          // q GEMM of tile i
+        const int s = i % S::NXS, bq = i % NSM;
+        tp = LP_T();
+        mbar_wait(&x_full[s], (uint32_t)((i / S::NXS) & 1), 413);
+        LP_ADD(7, tp);
+        tp = LP_T();
+        if (i >= NSM) mbar_wait(&q_empty[bq], (uint32_t)(((i / NSM) - 1) & 1), 414);
+        LP_ADD(8, tp);
+        tp = LP_T();
+        tc_fence_after();
+        if (leader) {
+          issue_mmas(tmem + (uint32_t)(bq * 128), x_lo + (uint32_t)((s * S::XSTAGE) >> 4), k_hi, (2 * LF_WP) >> 4, wq_lo, k_hi,
+                     (2 * LF_WP) >> 4, idesc1, C / 16, 0u);
+          umma_commit(&x_empty[s]);
+          umma_commit(&q_full[bq]);
+        }
+        __syncwarp();
+        LP_ADD(11, tp);
+      }
+      if (i >= NSM) {                                            // out GEMM of tile i - NSM
+        const int j = i - NSM, bs = j % NSM, bo = j & 1;         // Q tile of its softmax group, out accumulator j & 1
+        tp = LP_T();
+        mbar_wait(&s_full[bs], (uint32_t)((j / NSM) & 1), 415);
+        LP_ADD(9, tp);
+        tp = LP_T();
+        if (j >= 2) mbar_wait(&o_empty[bo], (uint32_t)(((j >> 1) - 1) & 1), 416);
+        LP_ADD(10, tp);
+        tp = LP_T();
+        tc_fence_after();
+        if (leader) {
+          issue_mmas(tmem + kOutCol + (uint32_t)(bo * C), q_lo + (uint32_t)((bs * 16 * LF_TP) >> 4), k_hi, (2 * LF_TP) >> 4, we_lo,
+                     k_hi, (2 * C * 16) >> 4, idesc3, 8, 0u);
+          umma_commit(&s_empty[bs]);
+          umma_commit(&o_full[bo]);
+        }
+        __syncwarp();
+        LP_ADD(11, tp);
+      }
+    }
+#ifdef IDIFF_PROF
+    if (prof && leader) { prof_buf[7] = pc[7]; prof_buf[8] = pc[8]; prof_buf[9] = pc[9]; prof_buf[10] = pc[10]; prof_buf[11] = pc[11]; prof_buf[14] = pc[14]; prof_buf[13] = pc[13]; }
+#endif
+  } else if (warp >= kSmWarp0 && warp < 16) {
+    // ------------------------------------------------ softmax groups ----------------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int g = (warp - kSmWarp0) >> 2;
+    float* wsum = par + 2 * C;
+    mbar_wait(w_bar, 0, 417);
+    if (tid - kSmWarp0 * 32 < 128) {                             // row sums of the bf16 Wq image (LayerNorm fold)
+      const int n = tid - kSmWarp0 * 32;
+      float acc = 0.f;
+#pragma unroll 4
+      for (int pl = 0; pl < C / 8; ++pl) {
+        float f[8];
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(sm + S::WQ + pl * LF_WP + n * 16), f);
+        acc += ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
+      }
+      wsum[n] = acc;
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(NSM * 128) : "memory");
+    uint8_t* qdst = sm + S::Q + g * 16 * LF_TP + px * 16;
+    for (int i = g, k = 0; i < ntiles; i += NSM, ++k) {
+      const float2 st = __ldg(sb + r_begin + i * LF_PX + px);
+      long long tp = LP_T();
+      mbar_wait(&q_full[g], (uint32_t)(k & 1), 418);
+      tc_fence_after();
+      LP_ADD(2, tp);
+      tp = LP_T();
+      if (k >= 1) mbar_wait(&s_empty[g], (uint32_t)((k - 1) & 1), 419);   // the previous out GEMM has read Q tile g
+      LP_ADD(3, tp);
+      tp = LP_T();
+      const float nmean = -st.x, rl = st.y * LF_LOG2E;
+      // one head (32 q channels of this thread's pixel) from raw accumulator registers; packed fp32x2 arithmetic:
+      // u = acc - mean * wsum (the rstd goes into the exponent), e = 2^(u rl - max rl), q = e * qscale / sum
+      auto head = [&](const uint32_t* r, int hd) {
+        float v[32];
+        f32x2 u[16];
+        const f32x2 nmean2 = pack2(nmean, nmean);
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 w = *reinterpret_cast<const float4*>(wsum + hd * 32 + q4 * 4);
+          u[q4 * 2] = fma2(nmean2, pack2(w.x, w.y), pack2(__uint_as_float(r[q4 * 4]), __uint_as_float(r[q4 * 4 + 1])));
+          u[q4 * 2 + 1] = fma2(nmean2, pack2(w.z, w.w), pack2(__uint_as_float(r[q4 * 4 + 2]), __uint_as_float(r[q4 * 4 + 3])));
+        }
+#pragma unroll
+        for (int p2 = 0; p2 < 16; ++p2) unpack2(u[p2], v[2 * p2], v[2 * p2 + 1]);
+        float m4[4] = {max3(v[0], v[1], v[2]), max3(v[3], v[4], v[5]), max3(v[6], v[7], v[8]), max3(v[9], v[10], v[11])};
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) m4[qq] = max3(m4[qq], v[12 + 2 * qq], v[13 + 2 * qq]);            // .. v[19]
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) m4[qq] = max3(m4[qq], v[20 + 3 * qq], max3(v[21 + 3 * qq], v[22 + 3 * qq], m4[qq]));  // .. v[31]
+        const float mneg = -fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * rl;   // rstd > 0: max commutes with the scaling
+        const f32x2 rl2 = pack2(rl, rl), mneg2 = pack2(mneg, mneg);
+        f32x2 s2a = pack2(0.f, 0.f), s2b = pack2(0.f, 0.f);
+#pragma unroll
+        for (int p2 = 0; p2 < 16; ++p2) {
+          float a0, a1;
+          unpack2(fma2(u[p2], rl2, mneg2), a0, a1);
+          u[p2] = pack2(ex2_fast(a0), ex2_fast(a1));
+          if (p2 & 1) s2b = add2(s2b, u[p2]); else s2a = add2(s2a, u[p2]);
+        }
+        float t0, t1;
+        unpack2(add2(s2a, s2b), t0, t1);
+        const float inv = qscale / (t0 + t1);
+        const f32x2 inv2 = pack2(inv, inv);
+#pragma unroll
+        for (int p2 = 0; p2 < 16; ++p2) unpack2(mul2(u[p2], inv2), v[2 * p2], v[2 * p2 + 1]);
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq)
+          *reinterpret_cast<uint4*>(qdst + (hd * 4 + gq) * LF_TP) = pack_bf16x8(v + gq * 8);
+      };
+      // TMEM is read at 16 B/clk per lane quadrant (a 32-column load = 256 cycles, shared with three other warps of the
+      // quadrant): the next head's columns are in flight while this one is worked on
+      const uint32_t qa = lane_base + (uint32_t)(g * 128);
+      uint32_t ra[32], rb[32];
+      tmem_ld32_async(qa, ra);
+      tmem_ld_wait32(ra);
+      tmem_ld32_async(qa + 32u, rb);
+      head(ra, 0);
+      tmem_ld_wait32(rb);
+      tmem_ld32_async(qa + 64u, ra);
+      head(rb, 1);
+      tmem_ld_wait32(ra);
+      tmem_ld32_async(qa + 96u, rb);
+      head(ra, 2);
+      tmem_ld_wait32(rb);
+      tc_fence_before();                                         // last TMEM read of this tile: hand the accumulator back
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_empty[g]);
+      head(rb, 3);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full[g]);
+      LP_ADD(4, tp);
+    }
+#ifdef IDIFF_PROF
+    if (prof && tid == kSmWarp0 * 32) { prof_buf[2] = pc[2]; prof_buf[3] = pc[3]; prof_buf[4] = pc[4]; }
+#endif
+  } else if (warp < kSmWarp0) {
+    // ------------------------------------------------ LayerNorm group(s) ------------------------------------
+    // out accumulator / barrier of tile i is i & 1; with one group (C = 64) it walks all tiles, with two each its parity
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const int g = warp >> 2;
+    const float invC = 1.f / (float)C;
+    for (int i = g; i < ntiles; i += NLN) {
+      const int bo = i & 1, k = i >> 1;
+      const uint32_t acc = lane_base + kOutCol + (uint32_t)(bo * C);
+      const size_t row = (size_t)(r_begin + i * LF_PX + px);
+      const uint4* rp = reinterpret_cast<const uint4*>(xb + row * C);
+      uint4* dp = reinterpret_cast<uint4*>(ob + row * C);
+      if constexpr (kOnePass) {
+        // C = 64: ONE pass over the accumulator (64 values stay in registers: half the TMEM reads of the two-pass
+        // version, and the accumulator is handed back before any arithmetic).  The residual x comes from the raw tile the
+        // TMA producer staged for the q GEMM (kResSmem; the stage ring then spans the whole pipeline), or from global
+        // memory in two halves of four 16 B loads (one LayerNorm group: 2390 instead of 1610 cycles per tile).
+        const int s = i % S::NXS;
+        const uint8_t* xs = sm + S::X + s * S::XSTAGE + px * 16;
+        uint4 rq[4];
+        if (!kResSmem) {
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) rq[gq] = __ldg(rp + gq);
+          prefetch_l2(rp + 4);
+        }
+        long long tp = LP_T();
+        mbar_wait(&o_full[bo], (uint32_t)(k & 1), 420);
+        if (kResSmem) mbar_wait(&x_full[s], (uint32_t)((i / S::NXS) & 1), 421);   // completed long ago: orders the TMA writes before the reads
+        tc_fence_after();
+        LP_ADD(5, tp);
+        tp = LP_T();
+        float v[64];
+        tmem_ld64(acc, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[bo]);
+        f32x2 sA = pack2(0.f, 0.f), sB = sA, tA = sA, tB = sA;
+#pragma unroll
+        for (int e4 = 0; e4 < 16; ++e4) {                        // y = acc + bias, sum y, sum y^2 (packed fp32x2)
+          const float4 bb = *reinterpret_cast<const float4*>(par + e4 * 4);
+          const f32x2 ya = add2(pack2(v[e4 * 4], v[e4 * 4 + 1]), pack2(bb.x, bb.y));
+          const f32x2 yb = add2(pack2(v[e4 * 4 + 2], v[e4 * 4 + 3]), pack2(bb.z, bb.w));
+          sA = add2(sA, ya); sB = add2(sB, yb);
+          tA = fma2(ya, ya, tA); tB = fma2(yb, yb, tB);
+          unpack2(ya, v[e4 * 4], v[e4 * 4 + 1]);
+          unpack2(yb, v[e4 * 4 + 2], v[e4 * 4 + 3]);
+        }
+        float s4[4], t4[4];
+        unpack2(sA, s4[0], s4[1]); unpack2(sB, s4[2], s4[3]);
+        unpack2(tA, t4[0], t4[1]); unpack2(tB, t4[2], t4[3]);
+        const float s1 = (s4[0] + s4[1]) + (s4[2] + s4[3]), s2 = (t4[0] + t4[1]) + (t4[2] + t4[3]);
+        const float mean = s1 * invC, var = fmaxf(s2 * invC - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        const f32x2 rstd2 = pack2(rstd, rstd), nmr2 = pack2(-mean * rstd, -mean * rstd);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          if (kResSmem) {
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) rq[gq] = *reinterpret_cast<const uint4*>(xs + (hf * 4 + gq) * LF_WP);
+          } else if (hf == 1) {
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) rq[gq] = __ldg(rp + 4 + gq);
+          }
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            const int pl = hf * 4 + gq;
+            float rr[8];
+            unpack_bf16x8(rq[gq], rr);
+            const float4 g0 = *reinterpret_cast<const float4*>(par + C + pl * 8);
+            const float4 g1 = *reinterpret_cast<const float4*>(par + C + pl * 8 + 4);
+            const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              const f32x2 o = fma2(fma2(pack2(v[pl * 8 + e], v[pl * 8 + e + 1]), rstd2, nmr2), pack2(gv[e], gv[e + 1]),
+                                   pack2(rr[e], rr[e + 1]));
+              unpack2(o, rr[e], rr[e + 1]);
+            }
+            dp[pl] = pack_bf16x8(rr);
+          }
+        }
+        if (kResSmem) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&x_empty[s]);                // this warp is done with the raw tile
+        }
+        LP_ADD(6, tp);
+        continue;
+      }
+      uint4 rq[4];                                               // residual x of the first chunk: in flight during the wait
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) rq[gq] = __ldg(rp + gq);
+      long long tp = LP_T();
+      mbar_wait(&o_full[bo], (uint32_t)(k & 1), 420);
+      tc_fence_after();
+      LP_ADD(5, tp);
+      tp = LP_T();
+      f32x2 sA = pack2(0.f, 0.f), sB = sA, tA = sA, tB = sA;
+#pragma unroll 1
+      for (int cc = 0; cc < C / 32; ++cc) {                      // pass A: LayerNorm statistics of (acc + bias)
+        float v[32];
+        tmem_ld32(acc + cc * 32, v);
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {                         // packed fp32x2: y = acc + bias, sum y, sum y^2
+          const float4 bb = *reinterpret_cast<const float4*>(par + cc * 32 + e4 * 4);
+          const f32x2 ya = add2(pack2(v[e4 * 4], v[e4 * 4 + 1]), pack2(bb.x, bb.y));
+          const f32x2 yb = add2(pack2(v[e4 * 4 + 2], v[e4 * 4 + 3]), pack2(bb.z, bb.w));
+          sA = add2(sA, ya); sB = add2(sB, yb);
+          tA = fma2(ya, ya, tA); tB = fma2(yb, yb, tB);
+        }
+      }
+      float s4[4], t4[4];
+      unpack2(sA, s4[0], s4[1]); unpack2(sB, s4[2], s4[3]);
+      unpack2(tA, t4[0], t4[1]); unpack2(tB, t4[2], t4[3]);
+      const float s1 = (s4[0] + s4[1]) + (s4[2] + s4[3]), s2 = (t4[0] + t4[1]) + (t4[2] + t4[3]);
+      const float mean = s1 * invC, var = fmaxf(s2 * invC - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      const f32x2 rstd2 = pack2(rstd, rstd), nmr2 = pack2(-mean * rstd, -mean * rstd);
+#pragma unroll 1
+      for (int cc = 0; cc < C / 32; ++cc) {                      // pass B: normalise, gain, + x, store
+        float v[32];
+        tmem_ld32(acc + cc * 32, v);
+        if (cc == C / 32 - 1) {                                   // last TMEM read: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_empty[bo]);
+        }
+        uint4 rn[4];
+        if (cc + 1 < C / 32) {                                    // next chunk's residual while this one is processed
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) rn[gq] = __ldg(rp + (cc + 1) * 4 + gq);
+        }
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          float rr[8];
+          unpack_bf16x8(rq[gq], rr);
+          const float4 b0 = *reinterpret_cast<const float4*>(par + cc * 32 + gq * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(par + cc * 32 + gq * 8 + 4);
+          const float4 g0 = *reinterpret_cast<const float4*>(par + C + cc * 32 + gq * 8);
+          const float4 g1 = *reinterpret_cast<const float4*>(par + C + cc * 32 + gq * 8 + 4);
+          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {                        // ((acc + bias) rstd - mean rstd) gain + x, two channels per op
+            const f32x2 y = add2(pack2(v[gq * 8 + e], v[gq * 8 + e + 1]), pack2(bv[e], bv[e + 1]));
+            const f32x2 o = fma2(fma2(y, rstd2, nmr2), pack2(gv[e], gv[e + 1]), pack2(rr[e], rr[e + 1]));
+            unpack2(o, rr[e], rr[e + 1]);
+          }
+          dp[cc * 4 + gq] = pack_bf16x8(rr);
+        }
+        if (cc + 1 < C / 32) {
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) rq[gq] = rn[gq];
+        }
+      }
+      LP_ADD(6, tp);
+    }
+#ifdef IDIFF_PROF
+    if (prof && tid == 0) { prof_buf[5] = pc[5]; prof_buf[6] = pc[6]; prof_buf[1] = (unsigned long long)ntiles; }
+#endif
+  }
+  tc_fence_before();
+  __syncthreads();
+#ifdef IDIFF_PROF
+  if (prof && tid == 0) prof_buf[0] = clock64() - t_kernel;
+#endif
+  if (warp == 17) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+#undef LP_T
+#undef LP_ADD
+}
+
+// tiles per CTA of la_out2: whole waves of one CTA per SM, and enough tiles to amortise the CTA's prologue (weights,
+// TMEM, wsum ~ 1.5 tile times)
+static int la_out2_tiles_per_cta(int B, int tiles_per_img, int num_sms) {
+  int best = tiles_per_img;
+  double best_score = -1.0;
+  for (int tpc = 2; tpc <= tiles_per_img; tpc *= 2) {
+    if (tiles_per_img % tpc) continue;
+    const long long ncta = (long long)B * (tiles_per_img / tpc);
+    const long long waves = (ncta + num_sms - 1) / num_sms;
+    const double score = (double)ncta / (double)(waves * num_sms) * tpc / (tpc + 1.5);
+    if (score > best_score + 1e-9) { best_score = score; best = tpc; }
+  }
+  return best;
+}
+
+unsigned long long* prof_buffer();   // conv_gemm.cu
+static unsigned long long* la_prof_buffer() {
+#ifdef IDIFF_PROF
+  const char* e = getenv("IDIFF_LA_PROF");
+  if (e && e[0] == '1') return prof_buffer();
+#endif
+  return nullptr;
+}
+
+static bool la_use_v1() {
+  static const int v1 = [] {
+    const char* e = getenv("IDIFF_LA_OUT_V1");                   // A/B switch: the two-CTA-per-SM output pass
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  return v1 != 0;
+}
+
 template <int C>
 static int launch_fused(const void* x, const float* stats, const void* wq, const void* wk, const float* wv,
                         const float* w_out, const float* bias, const float* gain, void* weff, void* out, float* scratch,
                         int B, int HW, float qscale, float eps, cudaStream_t st) {
   static DeviceOnce once;
+  int num_sms = 0;
   {
-    cudaError_t e = per_device_setup(once, nullptr, [] {
+    cudaError_t e = per_device_setup(once, &num_sms, [] {
       cudaError_t e2 = cudaFuncSetAttribute(la_ctx_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtxSmem<C>::TOTAL);
       if (e2 == cudaSuccess)
         e2 = cudaFuncSetAttribute(la_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, OutSmem<C>::TOTAL);
+      if (e2 == cudaSuccess)
+        e2 = cudaFuncSetAttribute(la_out2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Out2Smem<C>::TOTAL);
       return e2;
     });
     if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "linattn_fused attr: %s", cudaGetErrorString(e));
@@ -514,9 +1012,18 @@ static int launch_fused(const void* x, const float* stats, const void* wq, const
   la_merge_kernel<C><<<dim3(16, (unsigned)B), 256, 0, st>>>(part, pref, nchunk, wv, w_out,
                                                             reinterpret_cast<__nv_bfloat16*>(weff), HW);
   if (int rc = check_launch("la_merge")) return rc;
-  la_out_kernel<C><<<grid, 256, OutSmem<C>::TOTAL, st>>>(xb, sb, wq, reinterpret_cast<const __nv_bfloat16*>(weff), bias, gain,
-                                                         reinterpret_cast<__nv_bfloat16*>(out), HW, qscale, eps);
-  return check_launch("la_out");
+  if (la_use_v1()) {
+    la_out_kernel<C><<<grid, 256, OutSmem<C>::TOTAL, st>>>(xb, sb, wq, reinterpret_cast<const __nv_bfloat16*>(weff), bias, gain,
+                                                           reinterpret_cast<__nv_bfloat16*>(out), HW, qscale, eps);
+    return check_launch("la_out");
+  }
+  CUtensorMap tm_x;
+  if (int rc = make_map_2d(&tm_x, x, C, (long long)B * HW, C, 8, LF_PX)) return rc;
+  const int tiles_per_img = HW / LF_PX, tpc = la_out2_tiles_per_cta(B, tiles_per_img, num_sms > 0 ? num_sms : 148);
+  la_out2_kernel<C><<<dim3((unsigned)(tiles_per_img / tpc), (unsigned)B), LO2_THREADS, Out2Smem<C>::TOTAL, st>>>(
+      tm_x, xb, sb, wq, reinterpret_cast<const __nv_bfloat16*>(weff), bias, gain, reinterpret_cast<__nv_bfloat16*>(out), HW, tpc,
+      qscale, eps, la_prof_buffer());
+  return check_launch("la_out2");
 }
 
 }  // namespace idiff

@@ -123,7 +123,9 @@ def test_groupnorm_finalize_variants_agree(nets):
         out = alt(x, mu, 41.0, image_context=ctx)
         again = alt(x, mu, 41.0, image_context=ctx).clone()       # second pass on the self-cleaning sums
         assert torch.equal(out, again), kw
-        assert rel_err(out, ref) <= 2e-3, (kw, describe(out, ref, "gn variants"))
+        # statistics that differ in the last fp32 bits flip bf16 roundings downstream; through ~130 layers two equally
+        # valid paths end up as far apart as each is from the fp32 oracle (EPS_TOL)
+        assert rel_err(out, ref) <= EPS_TOL, (kw, describe(out, ref, "gn variants"))
 
 
 def test_time_tensor_and_wrapper_convention(nets):
