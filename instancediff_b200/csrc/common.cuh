@@ -72,6 +72,7 @@ IDIFF_DEVINL bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns
 // read only every 64 (long, hardware-suspended) polls.
 IDIFF_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity, int code) {
   if (mbar_try_wait(bar, parity)) return;
+  if (*((volatile int*)&g_watchdog) != 0) return;   // a tripped pipeline drains at once (not after 64 long polls per wait)
   uint64_t t0 = 0;
   uint32_t polls = 0;
   while (!mbar_try_wait_hint(bar, parity, IDIFF_MBAR_HINT_NS)) {

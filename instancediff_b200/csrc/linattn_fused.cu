@@ -33,6 +33,7 @@ constexpr int LF_XP = LF_PX * 16 + 16;          // x^ plane pitch: odd multiple 
 constexpr int LF_WP = 128 * 16;                 // weight plane (128 rows x 8 channels), verbatim packed image
 constexpr int LF_TP = 128 * 16;                 // E / Q staging plane (128 rows x 16 B)
 constexpr float LF_LOG2E = 1.4426950408889634f;
+constexpr int LO2_THREADS = 640;                // version-2 kernels: 5 warpgroups, one CTA per SM
 
 int watchdog_lattn(int clear) { return watchdog_read_tu(clear); }
 
@@ -232,6 +233,213 @@ la_ctx_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ st
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, S::TMEM_COLS);
+  }
+}
+
+// =====================================================================================================
+// pass 1, version 2: the same arithmetic (bit-identical partial sums), ONE CTA per SM with pipelined roles.
+//   warps 0-3 / 4-7 : two exponential groups, tiles of parity g.  A thread owns ONE k channel (TMEM lane) and all 128
+//                     pixels of the tile: the chunk's reference (channel maximum of the first tile) is thread-local.
+//                     e = exp(k - ref) -> E tile g (K-major A operand, K = pixels)
+//   warps 8-15      : x^ loaders (normalise on the way, as in version 1) into a ring of 4 (C = 64) / 3 (C = 128) stages
+//   warp 16         : Wk by one bulk copy;  warp 17: MMA issuer: k^T = Wk x^^T of tile i (accumulator i & 1), then
+//                     S += E [x^ | 1] of tile i - 2 (the x^ stage read MN-major)
+// Version 1 (2 CTAs x 8 warps per SM) ran store -> sync -> k GEMM -> wait -> exp -> sync -> S GEMM in lockstep: the
+// TMEM read port (16 B/clk per lane quadrant: 1024 cycles per tile) and the MUFU (1024 cycles per tile) idled two
+// thirds of the time.
+// =====================================================================================================
+template <int C>
+struct Ctx2Smem {
+  static constexpr int NP = C / 8 + 2;                         // x^ planes + the constant [1 | 0] planes
+  static constexpr int NXS = C == 64 ? 4 : 3;
+  static constexpr int XSTAGE = ((NP * LF_XP + 127) / 128) * 128;
+  static constexpr int X = 0, W = X + NXS * XSTAGE, E = W + (C / 8) * LF_WP, MAXV = E + 2 * 16 * LF_TP, BAR = MAXV + 128 * 4,
+                       TOTAL = BAR + 256;
+};
+
+template <int C>
+__global__ void __launch_bounds__(LO2_THREADS, 1)
+la_ctx2_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats, const void* __restrict__ wk,
+               float* __restrict__ pref, float* __restrict__ part, int HW) {
+  using S = Ctx2Smem<C>;
+  extern __shared__ __align__(128) uint8_t sm[];
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(sm + S::BAR);  // [4] x^ tile stored (8 loader warps)
+  uint64_t* x_empty = x_full + 4;                                // [4] S GEMM has read the stage
+  uint64_t* k_full = x_empty + 4;                                // [2] k accumulator complete
+  uint64_t* k_empty = k_full + 2;                                // [2] exponential group has read it
+  uint64_t* e_full = k_empty + 2;                                // [2] E tile written
+  uint64_t* e_empty = e_full + 2;                                // [2] S GEMM has read the E tile
+  uint64_t* w_bar = e_empty + 2;                                 // Wk landed
+  uint64_t* ref_bar = w_bar + 1;                                 // the chunk's reference is in shared memory
+  uint64_t* s_done = ref_bar + 1;                                // last S GEMM complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_done + 1);
+  float* kmax = reinterpret_cast<float*>(sm + S::MAXV);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x, b = blockIdx.y, nchunk = gridDim.x;
+  const int r_begin = chunk * lf_chunk(HW), r_end = min(HW, r_begin + lf_chunk(HW));
+  const int ntiles = (r_end - r_begin) / LF_PX;
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(&x_full[i], 8); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 4);
+      mbar_init(&e_full[i], 4); mbar_init(&e_empty[i], 1);
+    }
+    mbar_init(w_bar, 1); mbar_init(ref_bar, 4); mbar_init(s_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 17) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const __nv_bfloat16* xb = x + (size_t)b * HW * C;
+  const float2* sb = stats + (size_t)b * HW;
+  constexpr uint32_t kSCol = 256;                                // S | rowsum accumulator behind the two k accumulators
+
+  if (warp >= 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  if (warp == 16) {
+    // ------------------------------------------------ Wk ---------------------------------------------------
+    if (elect_one()) {
+      mbar_arrive_expect_tx(w_bar, (uint32_t)((C / 8) * LF_WP));
+      bulk_g2s(sm + S::W, wk, (uint32_t)((C / 8) * LF_WP), w_bar);
+    }
+  } else if (warp == 17) {
+    // ------------------------------------------------ MMA issuer --------------------------------------------
+    const bool leader = elect_one();
+    const uint32_t smem0 = smem_u32(sm);
+    const uint32_t idesc1 = umma_idesc_bf16(128, 128, 0);
+    const uint32_t idesc2 = umma_idesc_bf16(128, C + 16, 1);     // B = x^ tile read MN-major (channels contiguous)
+    const uint32_t w_lo = umma_desc_lo(smem0 + S::W, LF_WP), x_lo = umma_desc_lo(smem0 + S::X, LF_XP);
+    const uint32_t e_lo = umma_desc_lo(smem0 + S::E, LF_TP);
+    const uint32_t xm_lo = umma_desc_lo(smem0 + S::X, 128);      // MN-major view: LBO = 8-pixel group pitch
+    const uint32_t k_hi = umma_desc_hi(128), xm_hi = umma_desc_hi(LF_XP);
+    mbar_wait(w_bar, 0, 431);
+    tc_fence_after();
+    for (int i = 0; i < ntiles + 2; ++i) {
+      if (i < ntiles) {                                          // k GEMM of tile i
+        const int s = i % S::NXS, bk = i & 1;
+        mbar_wait(&x_full[s], (uint32_t)((i / S::NXS) & 1), 432);
+        if (i >= 2) mbar_wait(&k_empty[bk], (uint32_t)(((i >> 1) - 1) & 1), 433);
+        tc_fence_after();
+        if (leader) {
+          issue_mmas(tmem + (uint32_t)(bk * 128), w_lo, k_hi, (2 * LF_WP) >> 4, x_lo + (uint32_t)((s * S::XSTAGE) >> 4), k_hi,
+                     (2 * LF_XP) >> 4, idesc1, C / 16, 0u);
+          umma_commit(&k_full[bk]);
+        }
+        __syncwarp();
+      }
+      if (i >= 2) {                                              // S GEMM of tile i - 2 (in tile order: S accumulates)
+        const int j = i - 2, sj = j % S::NXS, bj = j & 1;
+        mbar_wait(&e_full[bj], (uint32_t)((j >> 1) & 1), 434);
+        tc_fence_after();
+        if (leader) {
+          issue_mmas(tmem + kSCol, e_lo + (uint32_t)((bj * 16 * LF_TP) >> 4), k_hi, (2 * LF_TP) >> 4,
+                     xm_lo + (uint32_t)((sj * S::XSTAGE) >> 4), xm_hi, 256 >> 4, idesc2, LF_PX / 16, j > 0 ? 1u : 0u);
+          umma_commit(&x_empty[sj]);
+          umma_commit(&e_empty[bj]);
+          if (j == ntiles - 1) umma_commit(s_done);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 8 && warp < 16) {
+    // ------------------------------------------------ x^ loaders --------------------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int ltid = tid - 256;
+    {                                                            // constant planes of every stage: ones (rowsum column), zeros
+      const uint32_t one2 = 0x3F803F80u;                         // bf16(1.0) x2
+      for (int st = 0; st < S::NXS; ++st) {
+        uint8_t* base = sm + S::X + st * S::XSTAGE;
+        if (ltid < 128) *reinterpret_cast<uint4*>(base + (C / 8) * LF_XP + ltid * 16) = make_uint4(one2, one2, one2, one2);
+        else *reinterpret_cast<uint4*>(base + (C / 8 + 1) * LF_XP + (ltid - 128) * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    XTile<C> xt;
+    if (ntiles > 0) xt.fetch(xb, sb, r_begin, ltid);
+    for (int i = 0; i < ntiles; ++i) {
+      const int s = i % S::NXS;
+      if (i >= S::NXS) mbar_wait(&x_empty[s], (uint32_t)(((i / S::NXS) - 1) & 1), 435);
+      xt.store(sm + S::X + s * S::XSTAGE, ltid);
+      if (i + 1 < ntiles) xt.fetch(xb, sb, r_begin + (i + 1) * LF_PX, ltid);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&x_full[s]);
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------ exponential groups ------------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const int g = warp >> 2, quarter = warp & 3, d = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    float mneg = 0.f;
+    for (int i = g, k = 0; i < ntiles; i += 2, ++k) {
+      mbar_wait(&k_full[g], (uint32_t)(k & 1), 436);
+      tc_fence_after();
+      const uint32_t ka = lane_addr + (uint32_t)(g * 128);
+      if (i == 0) {
+        // reference of this chunk = channel maximum over the first tile: all 128 pixels of channel d are this thread's
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          float v[32];
+          tmem_ld32(ka + j * 32, v);
+          float m4[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+          for (int qq = 4; qq < 32; ++qq) m4[qq & 3] = fmaxf(m4[qq & 3], v[qq]);
+          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+        }
+        pref[((size_t)b * nchunk + chunk) * 128 + d] = mx;
+        kmax[d] = mx;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ref_bar);                     // release: group 1 reads kmax after its wait
+      }
+      if (k == 0) {
+        if (g == 1) mbar_wait(ref_bar, 0, 437);
+        mneg = -kmax[d] * LF_LOG2E;
+      }
+      if (k >= 1) mbar_wait(&e_empty[g], (uint32_t)((k - 1) & 1), 438);    // the S GEMM of this group's previous tile has read E
+      uint8_t* edst = sm + S::E + g * 16 * LF_TP + d * 16;
+      // e = exp(k - ref) for this thread's k channel and the tile's 128 pixels -> K-major A tile [8-pixel group][d][8]
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        float v[32];
+        tmem_ld32(ka + j * 32, v);
+        if (j == 3) {                                            // last TMEM read of this tile: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&k_empty[g]);
+        }
+#pragma unroll
+        for (int qq = 0; qq < 32; ++qq) v[qq] = ex2_fast(fminf(fmaf(v[qq], LF_LOG2E, mneg), 86.5f));
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq)
+          *reinterpret_cast<uint4*>(edst + (j * 4 + gq) * LF_TP) = pack_bf16x8(v + gq * 8);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&e_full[g]);
+    }
+    if (g == 0) {                                                // rows d, columns [0, C] of S | rowsum
+      mbar_wait(s_done, 0, 439);
+      tc_fence_after();
+      float* dst = part + (((size_t)b * nchunk + chunk) * 128 + d) * (C + 1);
+      const uint32_t acc = lane_addr + kSCol;
+#pragma unroll 1
+      for (int cc = 0; cc < C / 32; ++cc) {
+        float v[32];
+        tmem_ld32(acc + cc * 32, v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) dst[cc * 32 + e] = v[e];
+      }
+      float v[32];
+      tmem_ld32(acc + C, v);                                     // column C = rowsum (the ones plane)
+      dst[C] = v[0];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -510,7 +718,6 @@ la_out_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ st
 // value.  Numerics: x enters the tensor core unnormalised (one bf16 rounding less than x^), the fold is exact in
 // fp32 up to the cancellation acc - mean * wsum (harmless while |mean| / std of a pixel's channels is far below 2^12).
 // =====================================================================================================
-constexpr int LO2_THREADS = 640;
 template <int C>
 struct Out2Smem {
   // Softmax is the long role (4 x (TMEM load + 32 exponentials + a shared-memory store) per pixel: ~5300 cycles per tile
@@ -976,12 +1183,14 @@ static unsigned long long* la_prof_buffer() {
   return nullptr;
 }
 
+// A/B switches, read at every call (a test flips them in-process): the two-CTA-per-SM version-1 passes
+static bool la_ctx_use_v1() {                                   // context pass: version 2 is bit-identical and measured equal
+  const char* e = getenv("IDIFF_LA_CTX_V2");                    // (0.464 vs 0.455 ms per C = 64 @256^2 block) -> version 1 stays the default
+  return !(e && e[0] == '1');
+}
 static bool la_use_v1() {
-  static const int v1 = [] {
-    const char* e = getenv("IDIFF_LA_OUT_V1");                   // A/B switch: the two-CTA-per-SM output pass
-    return (e && e[0] == '1') ? 1 : 0;
-  }();
-  return v1 != 0;
+  const char* e = getenv("IDIFF_LA_OUT_V1");
+  return e && e[0] == '1';
 }
 
 template <int C>
@@ -997,6 +1206,8 @@ static int launch_fused(const void* x, const float* stats, const void* wq, const
         e2 = cudaFuncSetAttribute(la_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, OutSmem<C>::TOTAL);
       if (e2 == cudaSuccess)
         e2 = cudaFuncSetAttribute(la_out2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Out2Smem<C>::TOTAL);
+      if (e2 == cudaSuccess)
+        e2 = cudaFuncSetAttribute(la_ctx2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ctx2Smem<C>::TOTAL);
       return e2;
     });
     if (e != cudaSuccess) return fail(IDIFF_ERR_CUDA, "linattn_fused attr: %s", cudaGetErrorString(e));
@@ -1007,7 +1218,8 @@ static int launch_fused(const void* x, const float* stats, const void* wq, const
   const dim3 grid((unsigned)nchunk, (unsigned)B);
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   const float2* sb = reinterpret_cast<const float2*>(stats);
-  la_ctx_kernel<C><<<grid, 256, CtxSmem<C>::TOTAL, st>>>(xb, sb, wk, pref, part, HW);
+  if (la_ctx_use_v1()) la_ctx_kernel<C><<<grid, 256, CtxSmem<C>::TOTAL, st>>>(xb, sb, wk, pref, part, HW);
+  else la_ctx2_kernel<C><<<grid, LO2_THREADS, Ctx2Smem<C>::TOTAL, st>>>(xb, sb, wk, pref, part, HW);
   if (int rc = check_launch("la_ctx")) return rc;
   la_merge_kernel<C><<<dim3(16, (unsigned)B), 256, 0, st>>>(part, pref, nchunk, wv, w_out,
                                                             reinterpret_cast<__nv_bfloat16*>(weff), HW);

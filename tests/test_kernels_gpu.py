@@ -207,6 +207,31 @@ def test_linattn_fused_matches_reference(shape):
     assert rel_err(out.float() - xf, ref - xf) <= 3e-2, describe(out.float() - xf, ref - xf, "linattn branch")
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 64, 64), (1, 32, 64, 128), (3, 16, 8, 64)])
+def test_linattn_pass_versions_agree(shape, monkeypatch):
+    """Version 2 of the two big passes (one pipelined CTA per SM) against version 1 (two lock-step CTAs per SM): the
+    context pass does the same arithmetic in the same order (bit-identical output), the output pass folds the
+    LayerNorm into the softmax instead of normalising x on CUDA cores (equal up to bf16 rounding of the operand)."""
+    from instancediff_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    B, H, W, Cc = shape
+    x = rand_act(B, H, W, Cc, g)
+    xf = x.float()
+    mean, var = xf.mean(-1, keepdim=True), xf.var(-1, unbiased=False, keepdim=True)
+    stats = torch.cat([mean, torch.rsqrt(var + 1e-5)], -1).reshape(-1, 2).contiguous()
+    args = (x, stats, ((torch.rand(384, Cc, generator=g) * 2 - 1) * (2.0 / Cc ** 0.5)).cuda(), (torch.rand(Cc, generator=g) + 0.5).cuda(),
+            ((torch.rand(Cc, 128, generator=g) * 2 - 1) / 128 ** 0.5).cuda(), (torch.rand(Cc, generator=g) - 0.5).cuda(),
+            (torch.rand(Cc, generator=g) + 0.5).cuda())
+    outs = {}
+    for ctx_v1, out_v1 in ((0, 0), (1, 0), (1, 1), (0, 1)):
+        monkeypatch.setenv("IDIFF_LA_CTX_V2", str(1 - ctx_v1))
+        monkeypatch.setenv("IDIFF_LA_OUT_V1", str(out_v1))
+        outs[(ctx_v1, out_v1)] = ops.linattn_fused(*args).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(outs[(0, 0)], outs[(1, 0)]) and torch.equal(outs[(0, 1)], outs[(1, 1)]), "context pass v2 != v1"
+    assert rel_err(outs[(0, 0)].float() - xf, outs[(0, 1)].float() - xf) <= 2e-2, "output pass v2 vs v1"
+
+
 def test_linattn_fused_reference_far_below_the_maximum():
     """The context pass exponentiates against the channel maximum of each chunk's FIRST tile (no k-max pre-pass).
     Adversarial input: every pixel of the first tile is anti-aligned with the k weights and a late pixel is aligned,

@@ -2,8 +2,8 @@
 # per-kernel table.  bash tools/gpu_check.sh <tag> [pytest -k expression]
 TAG=${1:-chk}; K=${2:-}
 mkdir -p gpurun_out; P=gpurun_out/${TAG}
-if [ -n "$K" ]; then timeout 900 python -m pytest tests -q -x -m gpu -p no:cacheprovider -k "$K" > ${P}_pytest.log 2>&1
-else timeout 900 python -m pytest tests -q -x -m gpu -p no:cacheprovider > ${P}_pytest.log 2>&1; fi
+if [ -n "$K" ]; then timeout 300 python -m pytest tests -q -x -m gpu -p no:cacheprovider -k "$K" > ${P}_pytest.log 2>&1
+else timeout 300 python -m pytest tests -q -x -m gpu -p no:cacheprovider > ${P}_pytest.log 2>&1; fi
 echo "pytest exit=$?"; tail -15 ${P}_pytest.log
 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-eager-baseline --dump-kernels ${P}_kernels.csv > ${P}_bench.json 2> ${P}_bench.err; echo "bench exit=$?"
 python - <<PY

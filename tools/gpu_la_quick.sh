@@ -1,8 +1,8 @@
 # linear attention: tests + stand-alone timing of both output-pass versions + launch list of v2
 mkdir -p gpurun_out; P=gpurun_out/${1:-laq}
-timeout 600 python -m pytest tests -q -x -m gpu -p no:cacheprovider -k "linattn or forward_layerwise" > ${P}_pytest.log 2>&1; echo "pytest exit=$?"; tail -3 ${P}_pytest.log
-python tools/run_linattn.py 2>&1 | tee ${P}_plain.log
-IDIFF_LA_OUT_V1=1 python tools/run_linattn.py 2>&1 | tee ${P}_plain_v1.log
+timeout 240 python -m pytest tests -q -x -m gpu -p no:cacheprovider -k "linattn or forward_layerwise" > ${P}_pytest.log 2>&1; echo "pytest exit=$?"; tail -3 ${P}_pytest.log
+timeout 120 python tools/run_linattn.py 2>&1 | tee ${P}_plain.log
+IDIFF_LA_OUT_V1=1 timeout 120 python tools/run_linattn.py 2>&1 | tee ${P}_plain_v1.log
 timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:'la_out' --csv --log-file ${P}_launches.csv python tools/run_linattn.py > /dev/null 2>&1; echo "list exit=$?"
 python - <<PY
 import csv,re
