@@ -192,7 +192,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ parti
 // with 128-row tiles the kernel was a chain of 16 dependent load -> reduce rounds per thread on 14 warps per SM.
 constexpr int CLG_ROWS = 32;
 template <int LPR>                                           // lanes per row = C / 8
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)                    // <= 64 registers: the inlined finalize had pushed it to 100 (2 CTAs per SM)
 chan_ln_gn_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gain, __nv_bfloat16* __restrict__ y,
                   float ln_eps, int HW, const GnFuse gf) {
   constexpr int C = LPR * 8, RPS = 256 / LPR, NR = CLG_ROWS / RPS;   // rows per sweep, rows per thread (4 / 2 / 1)
