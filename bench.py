@@ -385,6 +385,8 @@ def run_cuda(args):
     conv_labels = [label for kind, label, _, _, _ in rows if kind == "conv_gemm"]
     conv_traffic, traffic_src = conv_traffic_from_profile(conv_labels) if B == 32 and RES == 256 else (None, None)
     conv_algo_bytes = sum(nb for kind, _, _, _, nb in rows if kind == "conv_gemm")
+    la_rows = [(fl, ms, nb) for kind, _, fl, ms, nb in rows if kind == "linattn_fused"]
+    la_n, la_flops, la_ms, la_bytes = len(la_rows), sum(r[0] for r in la_rows), sum(r[1] for r in la_rows), sum(r[2] for r in la_rows)
     launches_per_fwd = plan.n_launch
     # per captured step: the plan's launches minus the two time-embedding kernels (their output is a table row copied by
     # the step-select kernel) plus step select and the fused SDE update
@@ -435,6 +437,13 @@ def run_cuda(args):
                                 "unit": "GB/s", "frac": split["1x1"]["bytes"] / (split["1x1"]["ms"] / 1e3) / 1e9 / pk["hbm"],
                                 "tflops": split["1x1"]["flops"] / (split["1x1"]["ms"] / 1e3) / 1e12,
                                 "launches_per_forward": split["1x1"]["n"], "ms_per_forward": split["1x1"]["ms"]},
+        "roofline_linattn": {"bound": "hbm", "kernel": "la_ctx + la_merge + la_out2 (fused linear attention blocks of the C = 64 / 128 levels)",
+                             "achieved": la_bytes / (la_ms / 1e3) / 1e9 if la_ms > 0 else None, "peak": pk["hbm"], "unit": "GB/s",
+                             "frac": (la_bytes / (la_ms / 1e3) / 1e9 / pk["hbm"]) if la_ms > 0 else None,
+                             "tflops": (la_flops / (la_ms / 1e3) / 1e12) if la_ms > 0 else None,
+                             "blocks_per_forward": la_n, "ms_per_forward": la_ms,
+                             "note": "algorithmic bytes = x read by both passes + the result + the row statistics; the measured bound is "
+                                     "the TMEM read port (16 B/clk per lane quadrant) and the MUFU, not HBM: DESIGN.md section 4"},
         "roofline_sde": {"bound": "hbm", "kernel": "sde_step_kernel", "achieved": sde_gbs, "peak": pk["hbm"], "unit": "GB/s",
                          "frac": sde_gbs / pk["hbm"], "us_per_launch": sde_us, "us_per_launch_eager": sde_us_eager,
                          "bytes_per_element": 16, "timing": f"CUDA events around 10 replays of a captured graph of launches rotating over {sde_sets} buffer sets "
