@@ -292,7 +292,10 @@ size_t idiff_linattn_scratch_floats(int B, int HW);
  *   ctx[h] = softmax_n(Wk x^)[h] (Wv x^)[h]^T / HW,  x^ = (x - mean) * rstd from row_stats [B*HW][2].
  * wq_packed / wk_packed: [128][C] weights with the pre-norm gain folded in, packed by pack_conv_weight(NT=128);
  * wv: fp32 [128][C] (gain folded); w_out: fp32 [C][128]; weff_scratch: bf16 [B][C*128]; scratch:
- * idiff_linattn_fused_scratch_floats(B, HW, C) floats.  HW must be a multiple of 128. */
+ * idiff_linattn_fused_scratch_floats(B, HW, C) floats.  HW must be a multiple of 128.
+ * The output pass runs as one pipelined CTA per SM (la_out2: TMA-fed raw tiles, the LayerNorm of x folded into the
+ * softmax as acc - mean * rowsum(Wq), result equal to the normalise-then-multiply form up to the bf16 rounding of x^);
+ * environment IDIFF_LA_OUT_V1=1 / IDIFF_LA_CTX_V2=1 select the other version of the output / context pass (A/B). */
 int idiff_linattn_fused(const void* x, const float* row_stats, const void* wq_packed, const void* wk_packed,
                         const float* wv, const float* w_out, const float* bias_out, const float* gain_out,
                         void* weff_scratch, void* out, float* scratch, int B, int HW, int C, float qscale, float ln_eps,
