@@ -292,7 +292,10 @@ struct Plan {
       const size_t bytes = (size_t)B * IDIFF_GN_SLOTS * 32 * 2 * 8;
       gn_sums = alloc(bytes);
       gn_arrivals = (unsigned int*)alloc(16);
-      if (gn_sums && gn_arrivals && (cudaMemset(gn_sums, 0, bytes) != cudaSuccess || cudaMemset(gn_arrivals, 0, 16) != cudaSuccess)) err = 1;
+      // plan-build time, once: the zeroing runs on the legacy stream, the plan's launches on the caller's (possibly
+      // non-blocking) stream -- make it complete before the first of them can start
+      if (gn_sums && gn_arrivals && (cudaMemset(gn_sums, 0, bytes) != cudaSuccess || cudaMemset(gn_arrivals, 0, 16) != cudaSuccess ||
+                                     cudaDeviceSynchronize() != cudaSuccess)) err = 1;
     }
     float* sc = (float*)tmp(std::string(tag) + "_sc", (size_t)B * C * 4);
     float* sh = (float*)tmp(std::string(tag) + "_sh", (size_t)B * C * 4);
