@@ -32,6 +32,33 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert L.idiff_sizeof_gemm_params() == ctypes.sizeof(_lib.GemmParams)
 
 
+def _struct_fields(name):
+    """member names of `typedef struct <name> { ... } <name>;` in include/idiff.h, in declaration order"""
+    text = open(os.path.join(ROOT, "include", "idiff.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    body = re.search(r"typedef struct %s\s*\{(.*?)\}\s*%s\s*;" % (name, name), text, flags=re.S).group(1)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(","):                      # `int32_t B, H, W` declares three members
+            fields.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", part)[-1])
+    return fields
+
+
+def test_ctypes_mirrors_follow_the_header_field_by_field():
+    """_lib.GemmParams / _lib.GnFuse against include/idiff.h: same members in the same order, same total size"""
+    import ctypes
+    from instancediff_b200 import _lib
+    L = _lib.lib()
+    for cname, mirror, sizeof in (("idiff_gemm_params", _lib.GemmParams, L.idiff_sizeof_gemm_params()),
+                                  ("idiff_gn_fuse", _lib.GnFuse, L.idiff_sizeof_gn_fuse())):
+        assert [f[0] for f in mirror._fields_] == _struct_fields(cname), cname
+        assert ctypes.sizeof(mirror) == sizeof, cname
+    assert _lib.GN_SLOTS == int(re.search(r"#define IDIFF_GN_SLOTS (\d+)", open(os.path.join(ROOT, "include", "idiff.h")).read()).group(1))
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from instancediff_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
